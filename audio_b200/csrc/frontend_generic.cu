@@ -1,0 +1,402 @@
+// Generic (any n_fft) fused STFT front end + workspace preparation + MFCC second stage.
+//
+// One CTA turns `2*pairs` consecutive frames of one utterance into power / complex / mel / dB
+// features without touching HBM in between:
+//   gather frame samples (pad / reflect index math in registers) x window
+//   -> two real frames packed as one complex signal (a + i b)
+//   -> n_fft-point complex Stockham FFT in shared memory, mixed radix, one output per thread per stage
+//   -> un-pack the two Hermitian spectra, scale, |.|^p into a shared power tile
+//   -> banded mel projection (each filter only visits its non-zero bins) -> optional dB / log.
+// Power-of-two n_fft take the register-FFT kernel in frontend_pow2.cu instead; this file is the
+// always-correct path for every other size and for two-sided / complex output.
+//
+// Reference semantics: src/torchaudio/functional/functional.py:54-145 (spectrogram),
+// transforms/_transforms.py:403-415 (MelScale), :701-705 (MFCC log/dB), functional.py:356-404.
+#include "common.cuh"
+
+namespace b200a {
+
+// ------------------------------------------------------------------------------------------
+// workspace preparation
+// ------------------------------------------------------------------------------------------
+__global__ void prepare_window_kernel(const float* __restrict__ window, int win_length, int n_fft,
+                                      int n_bins, int n_mels, int n_mfcc, int frame_length_norm,
+                                      int window_norm, WsHeader* hdr, float* padded) {
+  __shared__ double partial[256];
+  const int left = (n_fft - win_length) / 2;  // at::stft centres a short window
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_fft; i += blockDim.x) {
+    const int j = i - left;
+    const float w = (j >= 0 && j < win_length) ? window[j] : 0.f;
+    padded[i] = w;
+    acc += (double)w * (double)w;
+  }
+  partial[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) partial[threadIdx.x] += partial[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double scale = 1.0;
+    if (frame_length_norm) scale *= 1.0 / sqrt((double)n_fft);
+    if (window_norm) scale *= 1.0 / sqrt(partial[0]);
+    hdr->magic = kWsMagic;
+    hdr->n_fft = n_fft;
+    hdr->n_bins = n_bins;
+    hdr->n_mels = n_mels;
+    hdr->n_mfcc = n_mfcc;
+    hdr->scale = (float)scale;
+  }
+}
+
+__global__ void prepare_twiddle_kernel(int n_fft, float2* tw) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n_fft) {
+    double s, c;
+    sincospi(-2.0 * (double)q / (double)n_fft, &s, &c);
+    tw[q] = make_float2((float)c, (float)s);
+  }
+}
+
+// One thread per filter: copy the column and record its non-zero bin range [lo, hi).
+__global__ void prepare_fbank_kernel(const float* __restrict__ fb, int n_bins, int n_mels,
+                                     float* fb_copy, int2* bands) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_mels) return;
+  int lo = n_bins, hi = 0;
+  for (int k = 0; k < n_bins; ++k) {
+    const float v = fb[(size_t)k * n_mels + m];
+    fb_copy[(size_t)k * n_mels + m] = v;
+    if (v != 0.f) {
+      lo = min(lo, k);
+      hi = k + 1;
+    }
+  }
+  if (hi == 0) lo = 0;
+  bands[m] = make_int2(lo, hi);
+}
+
+__global__ void copy_kernel(const float* __restrict__ src, float* dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// generic fused kernel
+// ------------------------------------------------------------------------------------------
+struct GenericParams {
+  const float* wave;
+  int64_t length, row_stride;
+  int64_t frames;         // T
+  int64_t tiles_per_row;  // ceil(T / (2*pairs))
+  float* out;
+  float* group_max;
+  int64_t rows_per_group;
+  const float* window;  // [n_fft] centre padded
+  const float2* twiddle;
+  const int2* bands;
+  const float* fb;
+  const WsHeader* hdr;
+  int n_fft, hop, pad, center, pad_mode, n_bins, n_mels;
+  int pairs;
+  int n_stages;
+  int radix[kMaxStages];
+  int stage;  // b200a_stage
+  int log_mels;
+  float power, db_mult, db_amin, db_offset;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+__device__ __forceinline__ float spectral_power(float re, float im, float power) {
+  if (power == 2.f) return fmaf(re, re, im * im);
+  const float mag = hypotf(re, im);
+  if (power == 1.f) return mag;
+  return powf(mag, power);
+}
+
+__global__ void __launch_bounds__(256) stft_generic_kernel(const GenericParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = p.n_fft;
+  const int pairs = p.pairs;
+  float2* buf0 = reinterpret_cast<float2*>(smem_raw);
+  float2* buf1 = buf0 + (size_t)pairs * N;
+  float2* tw = buf1 + (size_t)pairs * N;
+
+  const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
+  const int64_t row = blockIdx.x / p.tiles_per_row;
+  const int64_t tile = blockIdx.x - row * p.tiles_per_row;
+  const int64_t t0 = tile * (2 * pairs);
+  const float* __restrict__ x = p.wave + row * p.row_stride;
+  const int half = p.center ? N / 2 : 0;
+
+  for (int i = tid; i < N; i += nthr) tw[i] = p.twiddle[i];
+
+  // ---- gather + window: z[n] = w[n] * (frame_a[n] + i frame_b[n]) --------------------------
+  for (int o = tid; o < pairs * N; o += nthr) {
+    const int pr = o / N, n = o - pr * N;
+    const int64_t ta = t0 + 2 * pr, tb = ta + 1;
+    const float w = p.window[n];
+    float a = 0.f, b = 0.f;
+    if (ta < p.frames) {
+      const int64_t s = source_index(ta * p.hop + n, p.length, p.pad, half, p.pad_mode);
+      if (s >= 0) a = x[s] * w;
+    }
+    if (tb < p.frames) {
+      const int64_t s = source_index(tb * p.hop + n, p.length, p.pad, half, p.pad_mode);
+      if (s >= 0) b = x[s] * w;
+    }
+    buf0[o] = make_float2(a, b);
+  }
+  __syncthreads();
+
+  // ---- Stockham autosort FFT, one output per thread per stage -----------------------------
+  float2* src = buf0;
+  float2* dst = buf1;
+  int Ns = 1;
+  for (int st = 0; st < p.n_stages; ++st) {
+    const int R = p.radix[st];
+    const int span = Ns * R;
+    const int NR = N / R;
+    const int step_stage = N / span;  // exponent step of the inter-stage twiddle
+    const int step_dft = NR;          // exponent step of the R-point DFT kernel
+    for (int o = tid; o < pairs * N; o += nthr) {
+      const int pr = o / N, i = o - pr * N;
+      const int blk = i / span, rem = i - blk * span;
+      const int q = rem / Ns, k = rem - q * Ns;
+      const float2* in = src + (size_t)pr * N + blk * Ns + k;
+      const int e1 = (k * step_stage + q * step_dft) % N;
+      float2 acc = in[0];
+      int e = e1;
+      for (int r = 1; r < R; ++r) {
+        const float2 v = in[(size_t)r * NR];
+        const float2 w = tw[e];
+        acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
+        acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
+        e += e1;
+        if (e >= N) e -= N;
+      }
+      dst[o] = acc;
+    }
+    __syncthreads();
+    float2* t = src;
+    src = dst;
+    dst = t;
+    Ns = span;
+  }
+  // `src` now holds Z[k] = A[k] + i B[k] in natural order; `dst` is free.
+  const float scale = p.hdr->scale;
+  const int n_bins = p.n_bins;
+  const float hs = 0.5f * scale;
+  float* tile_pow = reinterpret_cast<float*>(dst);  // [2*pairs][n_bins] (n_bins <= N, fits)
+
+  for (int o = tid; o < pairs * n_bins; o += nthr) {
+    const int pr = o / n_bins, k = o - pr * n_bins;
+    const float2 z = src[(size_t)pr * N + k];
+    const float2 zm = src[(size_t)pr * N + (k == 0 ? 0 : N - k)];
+    // A = (Z[k] + conj Z[N-k]) / 2,  B = (Z[k] - conj Z[N-k]) / (2i)
+    const float are = (z.x + zm.x) * hs, aim = (z.y - zm.y) * hs;
+    const float bre = (z.y + zm.y) * hs, bim = (zm.x - z.x) * hs;
+    const int64_t ta = t0 + 2 * pr, tb = ta + 1;
+    if (p.stage == B200A_STAGE_COMPLEX) {
+      float2* o2 = reinterpret_cast<float2*>(p.out);
+      if (ta < p.frames) o2[(row * p.frames + ta) * n_bins + k] = make_float2(are, aim);
+      if (tb < p.frames) o2[(row * p.frames + tb) * n_bins + k] = make_float2(bre, bim);
+    } else {
+      const float pa = spectral_power(are, aim, p.power);
+      const float pb = spectral_power(bre, bim, p.power);
+      if (p.stage == B200A_STAGE_POWER) {
+        if (ta < p.frames) p.out[(row * p.frames + ta) * n_bins + k] = pa;
+        if (tb < p.frames) p.out[(row * p.frames + tb) * n_bins + k] = pb;
+      } else {
+        tile_pow[(size_t)(2 * pr) * n_bins + k] = pa;
+        tile_pow[(size_t)(2 * pr + 1) * n_bins + k] = pb;
+      }
+    }
+  }
+  if (p.stage < B200A_STAGE_MEL) return;
+  __syncthreads();
+
+  // ---- banded mel projection (+ dB / log) ---------------------------------------------------
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+  float local_max = -CUDART_INF_F;
+  for (int f = warp; f < 2 * pairs; f += nwarps) {
+    const int64_t t = t0 + f;
+    if (t >= p.frames) break;
+    const float* pw = tile_pow + (size_t)f * n_bins;
+    float* orow = p.out + (row * p.frames + t) * p.n_mels;
+    for (int m = lane; m < p.n_mels; m += 32) {
+      const int2 band = p.bands[m];
+      float acc = 0.f;
+      for (int k = band.x; k < band.y; ++k) acc = fmaf(pw[k], p.fb[(size_t)k * p.n_mels + m], acc);
+      if (p.stage == B200A_STAGE_FEAT) {
+        acc = p.log_mels ? logf(acc + 1e-6f) : p.db_mult * log10f(fmaxf(acc, p.db_amin)) - p.db_offset;
+        local_max = fmaxf(local_max, acc);
+      }
+      orow[m] = acc;
+    }
+  }
+  if (p.stage == B200A_STAGE_FEAT && p.group_max != nullptr) {
+    local_max = warp_max(local_max);
+    if (lane == 0 && local_max > -CUDART_INF_F) atomic_max_f32(p.group_max + row / p.rows_per_group, local_max);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MFCC second stage: clamp at (group max - top_db), multiply by the DCT matrix
+// ------------------------------------------------------------------------------------------
+constexpr int kDctRowsPerBlock = 32;
+
+__global__ void __launch_bounds__(256)
+mfcc_finish_kernel(const float* __restrict__ feat, int64_t total_rows, int64_t frames, int n_mels,
+                   int n_mfcc, const float* __restrict__ dct, const float* __restrict__ group_max,
+                   int64_t rows_per_group, float top_db, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_dct = reinterpret_cast<float*>(smem_raw);       // [n_mels][n_mfcc]
+  float* s_feat = s_dct + (size_t)n_mels * n_mfcc;          // [rows][n_mels + 1]
+  const int ld = n_mels + 1;
+  const int64_t r0 = (int64_t)blockIdx.x * kDctRowsPerBlock;  // rows are (utterance, frame) pairs
+  const int rows = (int)min((int64_t)kDctRowsPerBlock, total_rows - r0);
+  for (int i = threadIdx.x; i < n_mels * n_mfcc; i += blockDim.x) s_dct[i] = dct[i];
+  for (int i = threadIdx.x; i < rows * n_mels; i += blockDim.x) {
+    const int r = i / n_mels, m = i - r * n_mels;
+    float v = feat[(r0 + r) * n_mels + m];
+    if (group_max != nullptr && top_db >= 0.f) {
+      const int64_t utt = (r0 + r) / frames;
+      v = fmaxf(v, group_max[utt / rows_per_group] - top_db);
+    }
+    s_feat[r * ld + m] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < rows * n_mfcc; i += blockDim.x) {
+    const int r = i / n_mfcc, c = i - r * n_mfcc;
+    float acc = 0.f;
+    for (int m = 0; m < n_mels; ++m) acc = fmaf(s_feat[r * ld + m], s_dct[m * n_mfcc + c], acc);
+    out[(r0 + r) * n_mfcc + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int factorize(int n, int* radix) {
+  int cnt = 0;
+  while (n % 4 == 0) { radix[cnt++] = 4; n /= 4; if (cnt >= kMaxStages) return -1; }
+  while (n % 2 == 0) { radix[cnt++] = 2; n /= 2; if (cnt >= kMaxStages) return -1; }
+  for (int f = 3; f * f <= n; f += 2)
+    while (n % f == 0) { radix[cnt++] = f; n /= f; if (cnt >= kMaxStages) return -1; }
+  if (n > 1) { if (cnt >= kMaxStages) return -1; radix[cnt++] = n; }
+  return cnt;
+}
+
+int validate_desc(const b200a_frontend_desc* d) {
+  if (d == nullptr) return B200A_EINVAL;
+  if (d->n_fft < 2 || d->hop < 1 || d->win_length < 1 || d->win_length > d->n_fft || d->pad < 0) return B200A_EINVAL;
+  if (d->n_fft > kMaxFft) return B200A_EUNSUPPORTED;
+  if (d->pad_mode < B200A_PAD_REFLECT || d->pad_mode > B200A_PAD_CIRCULAR) return B200A_EINVAL;
+  if (d->n_mels < 0 || d->n_mfcc < 0 || d->n_mfcc > d->n_mels) return B200A_EINVAL;
+  if (d->n_mels > 0 && !d->onesided) return B200A_EINVAL;
+  return B200A_OK;
+}
+
+int frontend_prepare_impl(const b200a_frontend_desc* d, const float* window, const float* fb,
+                          const float* dct, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  int rc = validate_desc(d);
+  if (rc != B200A_OK) return rc;
+  if (window == nullptr || ws == nullptr) return B200A_EINVAL;
+  if (d->n_mels > 0 && fb == nullptr) return B200A_EINVAL;
+  if (d->n_mfcc > 0 && dct == nullptr) return B200A_EINVAL;
+  const WsLayout l = ws_layout(*d);
+  if (ws_bytes < l.total) return B200A_EWORKSPACE;
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  const int n_bins = d->onesided ? d->n_fft / 2 + 1 : d->n_fft;
+  prepare_window_kernel<<<1, 256, 0, stream>>>(window, d->win_length, d->n_fft, n_bins, d->n_mels, d->n_mfcc,
+                                               d->frame_length_norm, d->window_norm,
+                                               reinterpret_cast<WsHeader*>(base + l.header),
+                                               reinterpret_cast<float*>(base + l.window));
+  prepare_twiddle_kernel<<<(d->n_fft + 255) / 256, 256, 0, stream>>>(d->n_fft, reinterpret_cast<float2*>(base + l.twiddle));
+  if (d->n_mels > 0) {
+    prepare_fbank_kernel<<<(d->n_mels + 63) / 64, 64, 0, stream>>>(fb, n_bins, d->n_mels,
+                                                                  reinterpret_cast<float*>(base + l.fb),
+                                                                  reinterpret_cast<int2*>(base + l.bands));
+  }
+  if (d->n_mfcc > 0) {
+    const int64_t n = (int64_t)d->n_mels * d->n_mfcc;
+    copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dct, reinterpret_cast<float*>(base + l.dct), n);
+  }
+  return launch_status();
+}
+
+int frontend_run_generic(const b200a_frontend_desc* d, const void* ws, int stage, const float* wave,
+                         int64_t rows, int64_t length, int64_t row_stride, int64_t frames, float* out,
+                         float* group_max, int64_t rows_per_group, cudaStream_t stream) {
+  const WsLayout l = ws_layout(*d);
+  const unsigned char* base = static_cast<const unsigned char*>(ws);
+  GenericParams p{};
+  p.n_stages = factorize(d->n_fft, p.radix);
+  if (p.n_stages < 0) return B200A_EUNSUPPORTED;
+  p.wave = wave;
+  p.length = length;
+  p.row_stride = row_stride;
+  p.frames = frames;
+  p.out = out;
+  p.group_max = group_max;
+  p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
+  p.window = reinterpret_cast<const float*>(base + l.window);
+  p.twiddle = reinterpret_cast<const float2*>(base + l.twiddle);
+  p.bands = reinterpret_cast<const int2*>(base + l.bands);
+  p.fb = reinterpret_cast<const float*>(base + l.fb);
+  p.hdr = reinterpret_cast<const WsHeader*>(base + l.header);
+  p.n_fft = d->n_fft;
+  p.hop = d->hop;
+  p.pad = d->pad;
+  p.center = d->center;
+  p.pad_mode = d->pad_mode;
+  p.n_bins = d->onesided ? d->n_fft / 2 + 1 : d->n_fft;
+  p.n_mels = d->n_mels;
+  p.stage = stage;
+  p.log_mels = d->log_mels;
+  p.power = d->power;
+  p.db_mult = d->db_multiplier;
+  p.db_amin = d->db_amin;
+  p.db_offset = d->db_offset;
+  // frames per CTA: enough work for 256 threads, at most ~48 KB of ping-pong buffers
+  int pairs = (int)(49152 / (16 * (size_t)d->n_fft));
+  if (pairs < 1) pairs = 1;
+  if (pairs > 8) pairs = 8;
+  while (pairs > 1 && (int64_t)2 * (pairs - 1) >= frames) --pairs;
+  p.pairs = pairs;
+  p.tiles_per_row = (frames + 2 * pairs - 1) / (2 * pairs);
+  const size_t smem = sizeof(float2) * (size_t)d->n_fft * (2 * pairs + 1);
+  static_assert(kMaxFft * 8 * 3 <= 227 * 1024, "largest FFT must fit in shared memory");
+  if (cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return B200A_ECUDA;
+  const int64_t grid = rows * p.tiles_per_row;
+  if (grid <= 0 || grid > 0x7fffffffLL) return B200A_EUNSUPPORTED;
+  stft_generic_kernel<<<(unsigned)grid, 256, smem, stream>>>(p);
+  return launch_status();
+}
+
+int mfcc_finish_impl(const b200a_frontend_desc* d, const void* ws, const float* feat, int64_t rows,
+                     int64_t frames, const float* group_max, int64_t rows_per_group, float top_db,
+                     float* out, cudaStream_t stream) {
+  const WsLayout l = ws_layout(*d);
+  const float* dct = reinterpret_cast<const float*>(static_cast<const unsigned char*>(ws) + l.dct);
+  const int64_t total = rows * frames;
+  if (total == 0) return B200A_OK;
+  const size_t smem = sizeof(float) * ((size_t)d->n_mels * d->n_mfcc + (size_t)kDctRowsPerBlock * (d->n_mels + 1));
+  if (smem > 200 * 1024) return B200A_EUNSUPPORTED;
+  if (cudaFuncSetAttribute(mfcc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+    return B200A_ECUDA;
+  const int64_t grid = (total + kDctRowsPerBlock - 1) / kDctRowsPerBlock;
+  if (grid > 0x7fffffffLL) return B200A_EUNSUPPORTED;
+  mfcc_finish_kernel<<<(unsigned)grid, 256, smem, stream>>>(feat, total, frames, d->n_mels, d->n_mfcc, dct, group_max,
+                                                            rows_per_group > 0 ? rows_per_group : 1, top_db, out);
+  return launch_status();
+}
+
+}  // namespace b200a

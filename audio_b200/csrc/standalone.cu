@@ -1,0 +1,93 @@
+// Stand-alone stages: MelScale on an existing spectrogram, AmplitudeToDB, fill.
+// These exist so the drop-in MelScale / AmplitudeToDB modules work on their own; the fused
+// front-end kernels never call them.
+// Reference: transforms/_transforms.py:403-415 (MelScale.forward), functional.py:356-404.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace b200a {
+
+// Lanes run along the frame axis (contiguous in the reference's logical (bins, frames) layout).
+__global__ void __launch_bounds__(256)
+apply_fbank_kernel(const float* __restrict__ spec, int64_t n_bins, int64_t frames, int64_t stride_row,
+                   int64_t stride_bin, int64_t stride_frame, const float* __restrict__ fb, int n_filters,
+                   float* __restrict__ out) {
+  const int64_t row = blockIdx.y;
+  const int64_t t = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  if (t >= frames) return;
+  const float* s = spec + row * stride_row + t * stride_frame;
+  for (int m = threadIdx.x >> 5; m < n_filters; m += blockDim.x >> 5) {
+    float acc = 0.f;
+    for (int64_t k = 0; k < n_bins; ++k) acc = fmaf(s[k * stride_bin], fb[k * n_filters + m], acc);
+    out[(row * frames + t) * n_filters + m] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+to_db_kernel(const float* __restrict__ x, int64_t group_elems, float mult, float amin, float offset,
+             float* group_max, float* __restrict__ out) {
+  const int64_t g = blockIdx.y;
+  const float* xi = x + g * group_elems;
+  float* oi = out + g * group_elems;
+  float local = -CUDART_INF_F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < group_elems; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = mult * log10f(fmaxf(xi[i], amin)) - offset;
+    oi[i] = v;
+    local = fmaxf(local, v);
+  }
+  if (group_max != nullptr) {
+    local = warp_max(local);
+    if ((threadIdx.x & 31) == 0 && local > -CUDART_INF_F) atomic_max_f32(group_max + g, local);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+clamp_floor_kernel(float* __restrict__ y, int64_t group_elems, const float* __restrict__ group_max, float top_db) {
+  const int64_t g = blockIdx.y;
+  const float floor_v = group_max[g] - top_db;
+  float* yi = y + g * group_elems;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < group_elems; i += (int64_t)gridDim.x * blockDim.x)
+    yi[i] = fmaxf(yi[i], floor_v);
+}
+
+__global__ void fill_kernel(float* dst, int64_t n, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+}
+
+int fill_impl(float* dst, int64_t n, float v, cudaStream_t stream) {
+  if (n <= 0) return B200A_OK;
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dst, n, v);
+  return launch_status();
+}
+
+int apply_fbank_impl(const float* spec, int64_t rows, int64_t n_bins, int64_t frames, int64_t stride_row,
+                     int64_t stride_bin, int64_t stride_frame, const float* fb, int n_filters, float* out,
+                     cudaStream_t stream) {
+  if (rows == 0 || frames == 0) return B200A_OK;
+  if (rows > 65535) return B200A_EUNSUPPORTED;
+  dim3 grid((unsigned)((frames + 31) / 32), (unsigned)rows);
+  apply_fbank_kernel<<<grid, 256, 0, stream>>>(spec, n_bins, frames, stride_row, stride_bin, stride_frame, fb, n_filters, out);
+  return launch_status();
+}
+
+int amplitude_to_db_impl(const float* x, int64_t groups, int64_t group_elems, float mult, float amin, float offset,
+                         float top_db, float* scratch, float* out, cudaStream_t stream) {
+  if (groups == 0 || group_elems == 0) return B200A_OK;
+  if (groups > 65535) return B200A_EUNSUPPORTED;
+  const bool clamp = top_db >= 0.f;
+  if (clamp) {
+    if (scratch == nullptr) return B200A_EINVAL;
+    int rc = fill_impl(scratch, groups, -INFINITY, stream);
+    if (rc != B200A_OK) return rc;
+  }
+  unsigned bx = (unsigned)((group_elems + 255) / 256);
+  if (bx > 1184) bx = 1184;  // 8 CTAs x 148 SMs, grid-stride beyond
+  dim3 grid(bx, (unsigned)groups);
+  to_db_kernel<<<grid, 256, 0, stream>>>(x, group_elems, mult, amin, offset, clamp ? scratch : nullptr, out);
+  if (clamp) clamp_floor_kernel<<<grid, 256, 0, stream>>>(out, group_elems, scratch, top_db);
+  return launch_status();
+}
+
+}  // namespace b200a

@@ -1,0 +1,234 @@
+"""Drop-in ``torchaudio.functional`` surface of the hot path, backed by libb200audio.so.
+
+Same names, argument order, defaults and error behaviour as the reference
+(/root/reference/src/torchaudio/functional/functional.py):
+``spectrogram`` (54-145), ``melscale_fbanks`` (518-587), ``linear_fbanks`` (590-633),
+``create_dct`` (636-667), ``amplitude_to_DB`` (356-404), ``resample`` (1435-1490) and the two
+private helpers ``transforms`` imports (``_get_sinc_resample_kernel`` 1305-1402,
+``_apply_sinc_resample_kernel`` 1405-1432).
+
+Differences, all explicit (never a silent fallback): CUDA float32 tensors only, forward only.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Optional, Union
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._bookkeeping import resample_ratio
+from ._constants import create_dct, linear_fbanks, melscale_fbanks, sinc_resample_kernel
+from ._plans import FrontendPlan, ResamplePlan, _no_autograd, _require_cuda_f32, _stream_ptr, new_group_max
+
+__all__ = [
+    "spectrogram",
+    "melscale_fbanks",
+    "linear_fbanks",
+    "create_dct",
+    "amplitude_to_DB",
+    "resample",
+    "mel_spectrogram",
+    "mfcc",
+]
+
+
+def _get_spec_norms(normalized: Union[str, bool]):
+    """(frame_length_norm, window_norm) -- reference functional.py:228-242."""
+    if isinstance(normalized, str):
+        if normalized not in ("frame_length", "window"):
+            raise ValueError("Invalid normalized parameter: {}".format(normalized))
+        return normalized == "frame_length", normalized == "window"
+    if isinstance(normalized, bool):
+        return False, normalized
+    raise TypeError("Input type not supported")
+
+
+def _unpack(out: Tensor, waveform: Tensor) -> Tensor:
+    """(rows, T, W[,2]) frame-major -> logical (..., W, T) view, as the reference returns it."""
+    lead = waveform.shape[:-1]
+    if out.dim() == 4:  # complex
+        out = torch.view_as_complex(out)
+    return out.reshape(lead + out.shape[-2:]).transpose(-1, -2)
+
+
+def spectrogram(
+    waveform: Tensor,
+    pad: int,
+    window: Tensor,
+    n_fft: int,
+    hop_length: int,
+    win_length: int,
+    power: Optional[float],
+    normalized: Union[bool, str],
+    center: bool = True,
+    pad_mode: str = "reflect",
+    onesided: bool = True,
+    return_complex: Optional[bool] = None,
+) -> Tensor:
+    """``(..., time) -> (..., freq, time)``; one fused kernel (pad, frame, window, FFT, |.|^p)."""
+    if return_complex is not None:
+        warnings.warn(
+            "`return_complex` argument is now deprecated and is not effective."
+            "`torchaudio.functional.spectrogram(power=None)` always returns a tensor with "
+            "complex dtype. Please remove the argument in the function call."
+        )
+    fl_norm, win_norm = _get_spec_norms(normalized)
+    desc = FrontendPlan.make_desc(n_fft, win_length, hop_length, pad, center, pad_mode, onesided, fl_norm, win_norm, power)
+    plan = FrontendPlan(desc)
+    ws = plan.workspace(window, None, None)
+    stage = _lib.STAGE_COMPLEX if power is None else _lib.STAGE_POWER
+    return _unpack(plan.run(ws, stage, waveform), waveform)
+
+
+def _db_groups(shape) -> int:
+    """How many independent top_db cut-offs the reference uses for a tensor of this shape
+    (functional.py:395-399: dims beyond the last three are separate items)."""
+    groups = 1
+    for s in shape[:-3]:
+        groups *= s
+    return groups
+
+
+def amplitude_to_DB(
+    x: Tensor, multiplier: float, amin: float, db_multiplier: float, top_db: Optional[float] = None
+) -> Tensor:
+    _require_cuda_f32(x, "x")
+    _no_autograd(x)
+    xc = x.contiguous()
+    out = torch.empty_like(xc)
+    if xc.numel() == 0:
+        return out
+    groups = _db_groups(xc.shape) if top_db is not None else 1
+    dev = xc.device
+    with torch.cuda.device(dev):
+        scratch = torch.empty(groups, dtype=torch.float32, device=dev)
+        rc = _lib.lib().b200a_amplitude_to_db(
+            xc.data_ptr(), groups, xc.numel() // groups, float(multiplier), float(amin),
+            float(multiplier) * float(db_multiplier), -1.0 if top_db is None else float(top_db),
+            scratch.data_ptr(), out.data_ptr(), _stream_ptr(dev),
+        )
+    _lib.check(rc, "amplitude_to_db")
+    return out
+
+
+def _apply_fbank(specgram: Tensor, fb: Tensor) -> Tensor:
+    """MelScale.forward on an existing spectrogram of logical shape (..., n_bins, T)."""
+    _require_cuda_f32(specgram, "specgram")
+    _require_cuda_f32(fb, "fb")
+    _no_autograd(specgram)
+    n_bins, frames = specgram.shape[-2], specgram.shape[-1]
+    if fb.shape[0] != n_bins:
+        raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied: n_bins={n_bins} vs fb {tuple(fb.shape)}")
+    lead = specgram.shape[:-2]
+    s3 = specgram.reshape((-1, n_bins, frames))
+    rows = s3.shape[0]
+    fbc = fb.contiguous()
+    dev = specgram.device
+    with torch.cuda.device(dev):
+        out = torch.empty((rows, frames, fb.shape[1]), dtype=torch.float32, device=dev)
+        rc = _lib.lib().b200a_apply_fbank(
+            s3.data_ptr(), rows, n_bins, frames, s3.stride(0), s3.stride(1), s3.stride(2),
+            fbc.data_ptr(), fb.shape[1], out.data_ptr(), _stream_ptr(dev),
+        )
+    _lib.check(rc, "apply_fbank")
+    return out.reshape(lead + out.shape[-2:]).transpose(-1, -2)
+
+
+# ---- fused MelSpectrogram / MFCC (what the transforms call) -----------------------------------
+def mel_spectrogram(plan: FrontendPlan, window: Tensor, fb: Tensor, waveform: Tensor) -> Tensor:
+    """Spectrogram + MelScale in ONE kernel: ``(..., time) -> (..., n_mels, time)``."""
+    ws = plan.workspace(window, fb, None)
+    return _unpack(plan.run(ws, _lib.STAGE_MEL, waveform), waveform)
+
+
+def mfcc(
+    plan: FrontendPlan,
+    window: Tensor,
+    fb: Tensor,
+    dct_mat: Tensor,
+    waveform: Tensor,
+    top_db: Optional[float],
+    log_mels: bool,
+    process_group=None,
+) -> Tensor:
+    """MelSpectrogram -> dB/log -> DCT: fused front-end kernel + clamp/DCT kernel.
+
+    The only cross-utterance coupling on the path is AmplitudeToDB's ``top_db`` clamp
+    (reference functional.py:395-399): for a waveform of dim <= 2 ONE maximum is shared by the
+    whole batch, for dim >= 3 each leading item has its own.  ``process_group`` (optional)
+    extends the shared maximum across ranks with one all-reduce(MAX) of that scalar.
+    """
+    ws = plan.workspace(window, fb, dct_mat)
+    rows = 1
+    for s in waveform.shape[:-1]:
+        rows *= s
+    clamp = (not log_mels) and top_db is not None
+    if clamp:
+        rows_per_group = waveform.shape[-2] if waveform.dim() >= 2 else 1
+        rows_per_group = max(int(rows_per_group), 1)
+        groups = max((rows + rows_per_group - 1) // rows_per_group, 1)
+        gmax = new_group_max(groups, waveform.device)
+    else:
+        rows_per_group, gmax = 1, None
+    feat = plan.run(ws, _lib.STAGE_FEAT, waveform, gmax, rows_per_group)
+    if clamp and process_group is not None and waveform.dim() <= 2:
+        import torch.distributed as dist
+
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=process_group)
+    out = plan.mfcc_finish(ws, feat, gmax, rows_per_group, top_db if clamp else None)
+    return _unpack(out, waveform)
+
+
+# ---- resampling ---------------------------------------------------------------------------------
+def _get_sinc_resample_kernel(
+    orig_freq: int,
+    new_freq: int,
+    gcd: int,
+    lowpass_filter_width: int = 6,
+    rolloff: float = 0.99,
+    resampling_method: str = "sinc_interp_hann",
+    beta: Optional[float] = None,
+    device: torch.device = torch.device("cpu"),
+    dtype: Optional[torch.dtype] = None,
+):
+    return sinc_resample_kernel(
+        orig_freq, new_freq, gcd, lowpass_filter_width, rolloff, resampling_method, beta, device, dtype
+    )
+
+
+def _apply_sinc_resample_kernel(
+    waveform: Tensor, orig_freq: int, new_freq: int, gcd: int, kernel: Tensor, width: int, plan: Optional[ResamplePlan] = None
+) -> Tensor:
+    if not waveform.is_floating_point():
+        raise TypeError(f"Expected floating point type for waveform tensor, but received {waveform.dtype}.")
+    if plan is None:
+        plan = ResamplePlan(int(orig_freq) // gcd, int(new_freq) // gcd, width)
+    return plan.run(kernel, waveform)
+
+
+def resample(
+    waveform: Tensor,
+    orig_freq: int,
+    new_freq: int,
+    lowpass_filter_width: int = 6,
+    rolloff: float = 0.99,
+    resampling_method: str = "sinc_interp_hann",
+    beta: Optional[float] = None,
+) -> Tensor:
+    if orig_freq <= 0.0 or new_freq <= 0.0:
+        raise ValueError("Original frequency and desired frequecy should be positive")
+    if orig_freq == new_freq:
+        return waveform
+    if not waveform.is_floating_point():
+        raise TypeError(f"Expected floating point type for waveform tensor, but received {waveform.dtype}.")
+    _require_cuda_f32(waveform, "waveform")
+    gcd = math.gcd(int(orig_freq), int(new_freq))
+    # the reference builds the taps on the waveform's device in its dtype (functional.py:1478-1488);
+    # that is a handful of tiny torch elementwise launches at call time -- table building, not the hot path
+    kernel, width = sinc_resample_kernel(
+        orig_freq, new_freq, gcd, lowpass_filter_width, rolloff, resampling_method, beta, waveform.device, waveform.dtype
+    )
+    return _apply_sinc_resample_kernel(waveform, orig_freq, new_freq, gcd, kernel, width)

@@ -1,0 +1,312 @@
+"""Drop-in ``torchaudio.transforms`` modules of the hot path, backed by libb200audio.so.
+
+Class names, constructor signatures, attribute / buffer / sub-module names and error
+behaviour follow /root/reference/src/torchaudio/transforms/_transforms.py
+(Spectrogram 25-123, AmplitudeToDB 300-346, MelScale 349-415, MelSpectrogram 506-622,
+MFCC 625-709, Resample 899-980), so ``state_dict``s interchange with torchaudio's and
+existing call sites keep working after ``import audio_b200.transforms as T``.
+
+``forward`` launches hand-written sm_100a kernels through the C ABI; MelSpectrogram and MFCC
+do NOT chain their sub-modules' forwards (that would round-trip the (B, T, n_fft/2+1) power
+spectrum through HBM) -- they read the sub-modules' buffers and launch the fused kernel.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Callable, Optional, Union
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from . import functional as F
+from ._plans import FrontendPlan, ResamplePlan
+
+__all__ = ["Spectrogram", "AmplitudeToDB", "MelScale", "MelSpectrogram", "MFCC", "Resample"]
+
+
+class Spectrogram(torch.nn.Module):
+    r"""Create a spectrogram from an audio signal: ``(..., time) -> (..., n_fft // 2 + 1, n_frames)``.
+
+    Args are those of ``torchaudio.transforms.Spectrogram`` (reference _transforms.py:64-78).
+    """
+
+    __constants__ = ["n_fft", "win_length", "hop_length", "pad", "power", "normalized"]
+
+    def __init__(
+        self,
+        n_fft: int = 400,
+        win_length: Optional[int] = None,
+        hop_length: Optional[int] = None,
+        pad: int = 0,
+        window_fn: Callable[..., Tensor] = torch.hann_window,
+        power: Optional[float] = 2.0,
+        normalized: Union[bool, str] = False,
+        wkwargs: Optional[dict] = None,
+        center: bool = True,
+        pad_mode: str = "reflect",
+        onesided: bool = True,
+        return_complex: Optional[bool] = None,
+    ) -> None:
+        super().__init__()
+        self.n_fft = n_fft
+        self.win_length = win_length if win_length is not None else n_fft
+        self.hop_length = hop_length if hop_length is not None else self.win_length // 2
+        window = window_fn(self.win_length) if wkwargs is None else window_fn(self.win_length, **wkwargs)
+        self.register_buffer("window", window)
+        self.pad = pad
+        self.power = power
+        self.normalized = normalized
+        self.center = center
+        self.pad_mode = pad_mode
+        self.onesided = onesided
+        if return_complex is not None:
+            warnings.warn(
+                "`return_complex` argument is now deprecated and is not effective."
+                "`torchaudio.transforms.Spectrogram(power=None)` always returns a tensor with "
+                "complex dtype. Please remove the argument in the function call."
+            )
+        self._plan: Optional[FrontendPlan] = None
+
+    def _frontend_plan(self, n_mels: int = 0, n_mfcc: int = 0, log_mels: bool = False) -> FrontendPlan:
+        fl_norm, win_norm = F._get_spec_norms(self.normalized)
+        desc = FrontendPlan.make_desc(
+            self.n_fft, self.win_length, self.hop_length, self.pad, self.center, self.pad_mode,
+            self.onesided, fl_norm, win_norm, self.power, n_mels, n_mfcc, log_mels,
+        )
+        return FrontendPlan(desc)
+
+    def forward(self, waveform: Tensor) -> Tensor:
+        plan = self._frontend_plan()
+        if self._plan is None or self._plan.desc.key() != plan.desc.key():
+            self._plan = plan
+        ws = self._plan.workspace(self.window, None, None)
+        stage = _lib.STAGE_COMPLEX if self.power is None else _lib.STAGE_POWER
+        return F._unpack(self._plan.run(ws, stage, waveform), waveform)
+
+
+class AmplitudeToDB(torch.nn.Module):
+    r"""Power/amplitude -> decibel scale (reference _transforms.py:300-346)."""
+
+    __constants__ = ["multiplier", "amin", "ref_value", "db_multiplier"]
+
+    def __init__(self, stype: str = "power", top_db: Optional[float] = None) -> None:
+        super().__init__()
+        self.stype = stype
+        if top_db is not None and top_db < 0:
+            raise ValueError("top_db must be positive value")
+        self.top_db = top_db
+        self.multiplier = 10.0 if stype == "power" else 20.0
+        self.amin = 1e-10
+        self.ref_value = 1.0
+        self.db_multiplier = math.log10(max(self.amin, self.ref_value))
+
+    def forward(self, x: Tensor) -> Tensor:
+        return F.amplitude_to_DB(x, self.multiplier, self.amin, self.db_multiplier, self.top_db)
+
+
+class MelScale(torch.nn.Module):
+    r"""STFT bins -> mel bins with triangular filters (reference _transforms.py:349-415)."""
+
+    __constants__ = ["n_mels", "sample_rate", "f_min", "f_max"]
+
+    def __init__(
+        self,
+        n_mels: int = 128,
+        sample_rate: int = 16000,
+        f_min: float = 0.0,
+        f_max: Optional[float] = None,
+        n_stft: int = 201,
+        norm: Optional[str] = None,
+        mel_scale: str = "htk",
+    ) -> None:
+        super().__init__()
+        self.n_mels = n_mels
+        self.sample_rate = sample_rate
+        self.f_max = f_max if f_max is not None else float(sample_rate // 2)
+        self.f_min = f_min
+        self.norm = norm
+        self.mel_scale = mel_scale
+        if f_min > self.f_max:
+            raise ValueError("Require f_min: {} <= f_max: {}".format(f_min, self.f_max))
+        fb = F.melscale_fbanks(n_stft, self.f_min, self.f_max, self.n_mels, self.sample_rate, self.norm, self.mel_scale)
+        self.register_buffer("fb", fb)
+
+    def forward(self, specgram: Tensor) -> Tensor:
+        return F._apply_fbank(specgram, self.fb)
+
+
+class MelSpectrogram(torch.nn.Module):
+    r"""MelSpectrogram for a raw audio signal, as ONE fused kernel.
+
+    Composes ``self.spectrogram`` and ``self.mel_scale`` exactly like the reference
+    (_transforms.py:557-610) so buffers are named ``spectrogram.window`` / ``mel_scale.fb``.
+    """
+
+    __constants__ = ["sample_rate", "n_fft", "win_length", "hop_length", "pad", "n_mels", "f_min"]
+
+    def __init__(
+        self,
+        sample_rate: int = 16000,
+        n_fft: int = 400,
+        win_length: Optional[int] = None,
+        hop_length: Optional[int] = None,
+        f_min: float = 0.0,
+        f_max: Optional[float] = None,
+        pad: int = 0,
+        n_mels: int = 128,
+        window_fn: Callable[..., Tensor] = torch.hann_window,
+        power: float = 2.0,
+        normalized: bool = False,
+        wkwargs: Optional[dict] = None,
+        center: bool = True,
+        pad_mode: str = "reflect",
+        onesided: Optional[bool] = None,
+        norm: Optional[str] = None,
+        mel_scale: str = "htk",
+    ) -> None:
+        super().__init__()
+        if onesided is not None:
+            warnings.warn(
+                "Argument 'onesided' has been deprecated and has no influence on the behavior of this module."
+            )
+        self.sample_rate = sample_rate
+        self.n_fft = n_fft
+        self.win_length = win_length if win_length is not None else n_fft
+        self.hop_length = hop_length if hop_length is not None else self.win_length // 2
+        self.pad = pad
+        self.power = power
+        self.normalized = normalized
+        self.n_mels = n_mels
+        self.f_max = f_max
+        self.f_min = f_min
+        self.spectrogram = Spectrogram(
+            n_fft=self.n_fft,
+            win_length=self.win_length,
+            hop_length=self.hop_length,
+            pad=self.pad,
+            window_fn=window_fn,
+            power=self.power,
+            normalized=self.normalized,
+            wkwargs=wkwargs,
+            center=center,
+            pad_mode=pad_mode,
+            onesided=True,
+        )
+        self.mel_scale = MelScale(
+            self.n_mels, self.sample_rate, self.f_min, self.f_max, self.n_fft // 2 + 1, norm, mel_scale
+        )
+        self._plan: Optional[FrontendPlan] = None
+
+    def _fused_plan(self, n_mfcc: int = 0, log_mels: bool = False, db=None) -> FrontendPlan:
+        if self.spectrogram.power is None:
+            raise RuntimeError("MelSpectrogram needs a real power spectrogram (power must not be None)")
+        plan = self.spectrogram._frontend_plan(self.mel_scale.fb.shape[1], n_mfcc, log_mels)
+        if db is not None:
+            plan.desc.db_multiplier, plan.desc.db_amin, plan.desc.db_offset = db
+        if self._plan is None or self._plan.desc.key() != plan.desc.key():
+            self._plan = plan
+        return self._plan
+
+    def forward(self, waveform: Tensor) -> Tensor:
+        plan = self._fused_plan()
+        return F.mel_spectrogram(plan, self.spectrogram.window, self.mel_scale.fb, waveform)
+
+
+class MFCC(torch.nn.Module):
+    r"""Mel-frequency cepstrum coefficients (reference _transforms.py:625-709).
+
+    ``process_group``: optional ``torch.distributed`` group.  When the batch of a 2-D
+    ``(batch, time)`` input is sharded across ranks, the reference's batch-global ``top_db``
+    clamp needs the maximum over ALL shards; setting the group makes ``forward`` all-reduce that
+    one scalar (MAX) between the two kernels.
+    """
+
+    __constants__ = ["sample_rate", "n_mfcc", "dct_type", "top_db", "log_mels"]
+
+    def __init__(
+        self,
+        sample_rate: int = 16000,
+        n_mfcc: int = 40,
+        dct_type: int = 2,
+        norm: str = "ortho",
+        log_mels: bool = False,
+        melkwargs: Optional[dict] = None,
+    ) -> None:
+        super().__init__()
+        supported_dct_types = [2]
+        if dct_type not in supported_dct_types:
+            raise ValueError("DCT type not supported: {}".format(dct_type))
+        self.sample_rate = sample_rate
+        self.n_mfcc = n_mfcc
+        self.dct_type = dct_type
+        self.norm = norm
+        self.top_db = 80.0
+        self.amplitude_to_DB = AmplitudeToDB("power", self.top_db)
+        melkwargs = melkwargs or {}
+        self.MelSpectrogram = MelSpectrogram(sample_rate=self.sample_rate, **melkwargs)
+        if self.n_mfcc > self.MelSpectrogram.n_mels:
+            raise ValueError("Cannot select more MFCC coefficients than # mel bins")
+        dct_mat = F.create_dct(self.n_mfcc, self.MelSpectrogram.n_mels, self.norm)
+        self.register_buffer("dct_mat", dct_mat)
+        self.log_mels = log_mels
+        self.process_group = None
+
+    def forward(self, waveform: Tensor) -> Tensor:
+        mel = self.MelSpectrogram
+        db = self.amplitude_to_DB
+        plan = mel._fused_plan(
+            self.dct_mat.shape[1], self.log_mels,
+            (float(db.multiplier), float(db.amin), float(db.multiplier * db.db_multiplier)),
+        )
+        return F.mfcc(
+            plan, mel.spectrogram.window, mel.mel_scale.fb, self.dct_mat, waveform,
+            db.top_db, self.log_mels, self.process_group,
+        )
+
+
+class Resample(torch.nn.Module):
+    r"""Resample a signal from one frequency to another (reference _transforms.py:899-980)."""
+
+    def __init__(
+        self,
+        orig_freq: int = 16000,
+        new_freq: int = 16000,
+        resampling_method: str = "sinc_interp_hann",
+        lowpass_filter_width: int = 6,
+        rolloff: float = 0.99,
+        beta: Optional[float] = None,
+        *,
+        dtype: Optional[torch.dtype] = None,
+    ) -> None:
+        super().__init__()
+        self.orig_freq = orig_freq
+        self.new_freq = new_freq
+        self.gcd = math.gcd(int(self.orig_freq), int(self.new_freq))
+        self.resampling_method = resampling_method
+        self.lowpass_filter_width = lowpass_filter_width
+        self.rolloff = rolloff
+        self.beta = beta
+        self._plan: Optional[ResamplePlan] = None
+        if self.orig_freq != self.new_freq:
+            kernel, self.width = F._get_sinc_resample_kernel(
+                self.orig_freq,
+                self.new_freq,
+                self.gcd,
+                self.lowpass_filter_width,
+                self.rolloff,
+                self.resampling_method,
+                beta,
+                dtype=dtype,
+            )
+            self.register_buffer("kernel", kernel)
+
+    def forward(self, waveform: Tensor) -> Tensor:
+        if self.orig_freq == self.new_freq:
+            return waveform
+        if self._plan is None:
+            self._plan = ResamplePlan(int(self.orig_freq) // self.gcd, int(self.new_freq) // self.gcd, self.width)
+        return F._apply_sinc_resample_kernel(
+            waveform, self.orig_freq, self.new_freq, self.gcd, self.kernel, self.width, self._plan
+        )

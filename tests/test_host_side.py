@@ -1,0 +1,228 @@
+"""CPU-only tests of the host side: constant builders (bit-identical with the reference's
+buffers), integer bookkeeping (Python and C), the C-ABI library (loads, exports every declared
+symbol, validates arguments without touching a GPU) and the drop-in module surface."""
+import ctypes
+import math
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+import torch
+from conftest import ROOT, assert_close
+from golden_cases import MEL_FB
+
+import audio_b200
+import audio_b200.functional as F
+import audio_b200.transforms as T
+from audio_b200 import _bookkeeping as bk
+from audio_b200 import _build, _lib
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _build.build()  # no-op when the .so is fresh
+    return _lib.lib()
+
+
+# ---------------- constants: bit-identical with the reference's buffers ------------------------
+def test_constants_bit_identical(ref_cases):
+    m = T.MelSpectrogram(16000, n_fft=1024, hop_length=256, n_mels=80)
+    assert np.array_equal(m.mel_scale.fb.numpy(), ref_cases["mel_c2_fb"])
+    assert np.array_equal(m.spectrogram.window.numpy(), ref_cases["mel_c2_window"])
+    m = T.MelSpectrogram(22050, n_fft=2048, hop_length=512, n_mels=128, norm="slaney", mel_scale="slaney", f_max=8000.0)
+    assert np.array_equal(m.mel_scale.fb.numpy(), ref_cases["mel_slaney2048_fb"])
+    mf = T.MFCC(16000, n_mfcc=40, melkwargs=dict(n_fft=1024, hop_length=256, n_mels=80))
+    assert np.array_equal(mf.dct_mat.numpy(), ref_cases["mfcc_dct"])
+    r = T.Resample(44100, 16000, resampling_method="sinc_interp_kaiser")
+    assert r.width == 17 and r.gcd == 100 and tuple(r.kernel.shape) == (160, 1, 475)
+    assert np.array_equal(r.kernel.numpy(), ref_cases["rs_kaiser_kernel"])
+    r = T.Resample(44100, 16000)
+    assert np.array_equal(r.kernel.numpy(), ref_cases["rs_hann_kernel"])
+
+
+@pytest.mark.parametrize("i", range(len(MEL_FB)))
+def test_melscale_fbanks_librosa(librosa_melfb, i):
+    c = MEL_FB[i]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fb = F.melscale_fbanks(c["n_fft"] // 2 + 1, c["fmin"], c["fmax"], c["n_mels"], c["sample_rate"], c["norm"], c["mel_scale"])
+    assert_close(fb.numpy(), librosa_melfb[f"fb_{i:02d}"], rtol=1.3e-6, atol=7e-5)
+
+
+def test_melscale_fbanks_warning_and_errors():
+    # reference functional_impl.py:1332-1349
+    with pytest.warns(UserWarning, match="At least one mel filterbank has all zero values"):
+        F.melscale_fbanks(201, 0.0, 8000.0, 128, 16000)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        F.melscale_fbanks(201, 0.0, 8000.0, 64, 16000)
+    with pytest.raises(ValueError):
+        F.melscale_fbanks(201, 0.0, 8000.0, 64, 16000, norm="other")
+    with pytest.raises(ValueError):
+        F.melscale_fbanks(201, 0.0, 8000.0, 64, 16000, mel_scale="other")
+    with pytest.raises(ValueError):
+        F.create_dct(13, 40, "other")
+
+
+def test_create_dct_norm_relation():
+    # reference transforms_test.py:157-173: ortho = none * sqrt(1/(2 n_mels)), row 0 * sqrt(1/(4 n_mels))
+    n_mfcc, n_mels = 40, 128
+    none = F.create_dct(n_mfcc, n_mels, None)
+    ortho = F.create_dct(n_mfcc, n_mels, "ortho")
+    assert torch.allclose(ortho[:, 0], none[:, 0] * math.sqrt(1 / (4 * n_mels)), atol=1e-6)
+    assert torch.allclose(ortho[:, 1:], none[:, 1:] * math.sqrt(1 / (2 * n_mels)), atol=1e-6)
+
+
+def test_resample_kernel_dtype_rules():
+    # transforms_test_impl.py:74-82 (cache dtype) + the float64-built/float32-stored default
+    k32, w = F._get_sinc_resample_kernel(16000, 8000, 8000)
+    assert k32.dtype == torch.float32 and w == math.ceil(6 * 2 / 0.99)
+    k64, _ = F._get_sinc_resample_kernel(16000, 8000, 8000, dtype=torch.float64)
+    assert k64.dtype == torch.float64
+    with pytest.raises(ValueError):
+        F._get_sinc_resample_kernel(16000, 8000, 8000, resampling_method="foo")
+    with pytest.raises(ValueError):
+        F._get_sinc_resample_kernel(16000, 8000, 8000, lowpass_filter_width=0)
+    with pytest.raises(Exception, match="integer type"):
+        F._get_sinc_resample_kernel(16000.5, 8000, 1)
+    with pytest.warns(UserWarning, match="deprecated"):
+        F._get_sinc_resample_kernel(16000, 8000, 8000, resampling_method="kaiser_window")
+
+
+# ---------------- integer bookkeeping: Python and C twins vs the reference ----------------------
+def test_frames_and_lengths_bit_exact(lib, ref_integers):
+    for L, n_fft, hop, center, pad, t in ref_integers["stft_frames"]:
+        L, n_fft, hop, center, pad, t = map(int, (L, n_fft, hop, center, pad, t))
+        assert bk.num_frames(L, n_fft, hop, bool(center), pad) == t, (L, n_fft, hop, center, pad)
+        assert lib.b200a_num_frames(L, n_fft, hop, center, pad) == t
+    for o, n, L, w, taps, out_len in ref_integers["resample"]:
+        o_r, n_r, g = bk.resample_ratio(int(o), int(n))
+        assert bk.resample_width(o_r, n_r, 6, 0.99) == w == lib.b200a_resample_width(o_r, n_r, 6, 0.99)
+        assert 2 * w + o_r == taps
+        assert bk.resample_len(int(L), o_r, n_r) == out_len == lib.b200a_resample_len(int(L), o_r, n_r)
+
+
+def test_pad_index_matches_torch_pad(lib):
+    n, h = 11, 4
+    x = torch.arange(n, dtype=torch.float32)[None, None]
+    for mode_name, mode in _lib.PAD_MODE.items():
+        ref = torch.nn.functional.pad(x + 1, (h, h), mode=mode_name)[0, 0]  # +1 so zero == padding
+        for i in range(-h, n + h):
+            j_c = lib.b200a_pad_index(i, n, mode)
+            j_py = bk.pad_index(i, n, mode)
+            assert j_c == j_py
+            assert ref[i + h].item() == (0.0 if j_c < 0 else float(j_c + 1)), (mode_name, i)
+
+
+def test_shard_bounds_partition():
+    for total in (0, 1, 7, 256, 2048, 2049):
+        for world in (1, 2, 3, 8):
+            spans = [bk.shard_bounds(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+# ---------------- the C ABI library ---------------------------------------------------------------
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "b200audio.h")).read()
+    declared = set(re.findall(r"^(?:int|size_t|int64_t|int32_t|const char\*)\s+(b200a_[a-z0-9_]+)\(", header, re.M))
+    assert declared, "no declarations parsed"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in include/b200audio.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), "ctypes table and header disagree"
+    assert lib.b200a_version() == 100
+    assert ctypes.sizeof(_lib.FrontendDesc) == 16 * 4
+
+
+def test_abi_argument_validation_without_gpu(lib):
+    d = _lib.FrontendDesc()
+    assert lib.b200a_frontend_workspace_bytes(d) == 0  # all-zero descriptor is invalid
+    good = T.Spectrogram(n_fft=512)._frontend_plan().desc
+    assert lib.b200a_frontend_workspace_bytes(good) > 512 * 4 + 512 * 8
+    # null pointers / bad sizes are rejected before any CUDA call
+    assert lib.b200a_frontend_run(good, None, 1, None, 1, 1000, 1000, None, None, 1, None) == _lib.EINVAL
+    assert lib.b200a_frontend_prepare(good, None, None, None, None, 0, None) == _lib.EINVAL
+    assert lib.b200a_resample_run(None, None, 441, 160, 17, None, 1, 10, 10, None, 10, 4, None) == _lib.EINVAL
+    assert lib.b200a_fill_f32(None, 4, 0.0, None) == _lib.EINVAL
+    bad = T.Spectrogram(n_fft=512)._frontend_plan().desc
+    bad.hop = 0
+    assert lib.b200a_frontend_workspace_bytes(bad) == 0
+    big = T.Spectrogram(n_fft=16384)._frontend_plan().desc
+    assert lib.b200a_frontend_workspace_bytes(big) == 0  # > 8192 is documented as unsupported
+    for code in (0, -1, -2, -3, -4, -5, -99):
+        assert isinstance(lib.b200a_strerror(code), bytes)
+    assert lib.b200a_num_bins(1024, 1) == 513 and lib.b200a_num_bins(1024, 0) == 1024
+
+
+# ---------------- drop-in module surface ----------------------------------------------------------
+def test_state_dict_names_match_reference():
+    # transforms_test.py:68-85
+    m = T.MelSpectrogram()
+    assert set(m.state_dict()) == {"spectrogram.window", "mel_scale.fb"}
+    mf = T.MFCC()
+    assert set(mf.state_dict()) == {"MelSpectrogram.spectrogram.window", "MelSpectrogram.mel_scale.fb", "dct_mat"}
+    assert set(T.Resample(16000, 8000).state_dict()) == {"kernel"}
+    assert set(T.Resample(16000, 16000).state_dict()) == set()
+    assert set(T.Spectrogram().state_dict()) == {"window"}
+    assert set(T.MelScale().state_dict()) == {"fb"}
+
+
+def test_defaults_and_attributes():
+    s = T.Spectrogram()
+    assert (s.n_fft, s.win_length, s.hop_length, s.pad, s.power, s.normalized) == (400, 400, 200, 0, 2.0, False)
+    assert (s.center, s.pad_mode, s.onesided) == (True, "reflect", True)
+    m = T.MelSpectrogram()
+    assert (m.sample_rate, m.n_fft, m.n_mels, m.f_min, m.f_max, m.hop_length) == (16000, 400, 128, 0.0, None, 200)
+    assert m.mel_scale.f_max == 8000.0 and tuple(m.mel_scale.fb.shape) == (201, 128)
+    mf = T.MFCC()
+    assert (mf.n_mfcc, mf.dct_type, mf.norm, mf.top_db, mf.log_mels) == (40, 2, "ortho", 80.0, False)
+    assert mf.amplitude_to_DB.multiplier == 10.0 and mf.amplitude_to_DB.db_multiplier == 0.0
+    r = T.Resample(44100, 16000)
+    assert (r.orig_freq, r.new_freq, r.gcd, r.lowpass_filter_width, r.rolloff) == (44100, 16000, 100, 6, 0.99)
+    a = T.AmplitudeToDB("magnitude", 80.0)
+    assert a.multiplier == 20.0 and a.amin == 1e-10 and a.ref_value == 1.0
+
+
+def test_constructor_errors_match_reference():
+    with pytest.raises(ValueError, match="DCT type not supported"):
+        T.MFCC(dct_type=3)
+    with pytest.raises(ValueError, match="Cannot select more MFCC coefficients"):
+        T.MFCC(n_mfcc=60, melkwargs=dict(n_mels=40))
+    with pytest.raises(ValueError, match="top_db must be positive"):
+        T.AmplitudeToDB(top_db=-1.0)
+    with pytest.raises(ValueError, match="Require f_min"):
+        T.MelScale(f_min=9000.0, f_max=100.0)
+    with pytest.raises(ValueError, match="Invalid resampling method"):
+        T.Resample(16000, 8000, resampling_method="foo")
+    with pytest.raises(ValueError, match="Invalid normalized parameter"):
+        F._get_spec_norms("energy")
+    with pytest.raises(TypeError):
+        F._get_spec_norms(1.0)
+    with pytest.warns(UserWarning, match="onesided"):
+        T.MelSpectrogram(onesided=True)
+    with pytest.warns(UserWarning, match="return_complex"):
+        T.Spectrogram(return_complex=True)
+
+
+def test_no_cpu_fallback():
+    x = torch.randn(2, 4000)
+    for mod in (T.Spectrogram(), T.MelSpectrogram(), T.MFCC(), T.Resample(16000, 8000), T.AmplitudeToDB()):
+        with pytest.raises(RuntimeError, match="no CPU or ATen fallback"):
+            mod(x)
+    with pytest.raises(RuntimeError, match="no CPU or ATen fallback"):
+        F.resample(x, 16000, 8000)
+    with pytest.raises(ValueError):
+        F.resample(x, 0, 8000)
+    assert F.resample(x, 8000, 8000) is x  # identity fast path (functional.py:1471-1472)
+    assert T.Resample(8000, 8000)(x) is x
+    with pytest.raises(TypeError, match="Expected floating point type"):
+        F.resample(torch.zeros(4, dtype=torch.int32), 16000, 8000)
+
+
+def test_library_path_is_in_tree():
+    assert audio_b200.library_path().startswith(ROOT)
