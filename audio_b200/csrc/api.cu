@@ -97,6 +97,7 @@ int b200a_frontend_run(const b200a_frontend_desc* desc, const void* workspace, i
                        int64_t rows_per_group, b200a_stream stream) {
   int rc = validate_desc(desc);
   if (rc != B200A_OK) return rc;
+  if (rows == 0) return B200A_OK;  // empty batch: nothing to enqueue (pointers may be null)
   if (workspace == nullptr || wave == nullptr || out == nullptr) return B200A_EINVAL;
   if (rows < 0 || length < 0 || row_stride < length) return B200A_EINVAL;
   if (stage < B200A_STAGE_COMPLEX || stage > B200A_STAGE_FEAT) return B200A_EINVAL;

@@ -114,9 +114,9 @@ int resample_prepare_impl(const float* kernel, int orig_r, int new_r, int width,
 int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r, int width, const float* wave,
                       int64_t rows, int64_t length, int64_t row_stride, float* out, int64_t out_row_stride,
                       int64_t out_len, cudaStream_t stream) {
-  if (ws == nullptr || kernel == nullptr || wave == nullptr || out == nullptr) return B200A_EINVAL;
   if (orig_r < 1 || new_r < 1 || width < 0 || rows < 0 || length < 0 || out_len < 0) return B200A_EINVAL;
-  if (rows == 0 || out_len == 0) return B200A_OK;
+  if (rows == 0 || out_len == 0) return B200A_OK;  // empty batch: pointers may be null
+  if (ws == nullptr || kernel == nullptr || wave == nullptr || out == nullptr) return B200A_EINVAL;
   if (rows > 65535) return B200A_EUNSUPPORTED;
   const int taps = 2 * width + orig_r;
   const RsLayout l = rs_layout(new_r, taps);

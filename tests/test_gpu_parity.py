@@ -329,11 +329,12 @@ def test_config3_full_size_properties():
     z = r(x[:2, 441:])
     assert torch.equal(z[:, 100:70000], y[:2, 260:70160])
     # a band-limited tone passes with unit gain (filter rows sum to 1)
-    t = torch.arange(L, device=DEV) / 44100.0
-    tone = torch.sin(2 * math.pi * 1000.0 * t)[None]
+    # (phases are formed in float64: 2 pi 1000 t reaches 3e4 rad, beyond float32 resolution)
+    t = torch.arange(L, device=DEV, dtype=torch.float64) / 44100.0
+    tone = torch.sin(2 * math.pi * 1000.0 * t).float()[None]
     out = r(tone)[0, 1000:-1000]
-    t2 = torch.arange(80000, device=DEV)[1000:-1000] / 16000.0
-    assert torch.allclose(out, torch.sin(2 * math.pi * 1000.0 * t2), atol=2e-3)
+    t2 = torch.arange(80000, device=DEV, dtype=torch.float64)[1000:-1000] / 16000.0
+    assert torch.allclose(out, torch.sin(2 * math.pi * 1000.0 * t2).float(), atol=2e-3)
     exp = O.resample(x[:2].cpu().numpy(), 44100, 16000, resampling_method="sinc_interp_kaiser")
     assert np.abs(host(y[:2]) - exp).max() <= 1e-4 * np.abs(exp).max()
 
