@@ -1,15 +1,28 @@
 // Register-FFT fast path of the fused front end (n_fft = 1024, one-sided, real output stages).
 //
-// One WARP transforms one PAIR of consecutive frames (a, b) of an utterance:
-//   z[n] = w[n] * (a[n] + i b[n]),  n = lane + 32 j          -- 32 complex values per lane, coalesced loads
+// One WARP transforms one PAIR of consecutive frames (a, b) of an utterance; a CTA of 8 warps
+// therefore finishes 16 frames per iteration:
+//   input   the 1024+hop contiguous samples of the pair are staged into shared memory by ONE
+//           bulk async copy (cp.async.bulk + mbarrier, the TMA engine's 1-D mode), issued one
+//           iteration ahead so its latency hides behind the previous pair's arithmetic
+//   z[n] = w[n] * (a[n] + i b[n]),  n = lane + 32 j      -- 32 complex values per lane
 //   pass 1  32-point DFT over j in registers (radix-2 DIT, compile-time twiddles, FMA-form butterflies)
-//   twiddle W_1024^(lane * k2) from a shared 32x32 table
-//   transpose through a per-warp padded shared tile (the only exchange of the whole FFT)
+//   twiddle W_1024^(lane * k2) from a shared 32x32 table, transpose through a padded per-warp tile
 //   pass 2  32-point DFT over the former lane index in registers  -> Z[lane + 32 k1]
 //   un-pack the two real spectra with one shuffle per needed value:  A = (Z[k] + conj Z[N-k]) / 2,
 //                                                                    B = (Z[k] - conj Z[N-k]) / 2i
-//   |.|^p -> global (Spectrogram) or -> the warp's shared tile -> banded mel (-> dB / log) -> global.
+//   |.|^p -> global (Spectrogram), or -> a shared [16 frames x 520 bins] power tile.
+//   mel     all 8 warps then contract the power tile with the filterbank on the tensor pipe:
+//           warp-level mma.sync m16n8k8 TF32 with error-compensated operands
+//           (P_hi*F_hi + P_lo*F_hi + P_hi*F_lo, ~2^-21 relative), visiting only the k-steps where a
+//           group of 8 filters is non-zero; (-> dB / log) -> global.
 // Nothing but the waveform is read from HBM and nothing but the final features is written.
+//
+// Why mma.sync and not tcgen05 for the mel contraction: a tcgen05.mma tile needs M >= 64 frames of
+// the A operand resident (64 x 513 power values in two bf16 planes or one fp32 plane = 131 KB, or
+// > 512 TMEM columns) next to the FFT working set of the warps that produce them; that does not fit
+// the 227 KB of shared memory per SM at n_fft = 1024.  The warp-level fragment MMA has M = 16, which is
+// exactly one CTA iteration.  See DESIGN.md ("mel projection").
 //
 // Reference semantics: src/torchaudio/functional/functional.py:54-145 and
 // transforms/_transforms.py:403-415, :701-705 (see frontend_generic.cu for the any-size path).
@@ -24,28 +37,54 @@ namespace {
 constexpr int kN = 1024;
 constexpr int kBins = kN / 2 + 1;
 constexpr int kWarps = 8;
+constexpr int kSlots = 2 * kWarps;               // frames finished per CTA iteration
 constexpr int kTileLd = 33;                      // float2 row pitch of the transpose tile (bank-conflict free)
 constexpr int kTileFloat2 = 32 * kTileLd;        // per warp
-constexpr int kPowLd = 520;                      // float pitch of one frame's power row inside the same tile
-constexpr int kCsrSmemMax = 6144;                // filterbank weights kept in shared memory up to this many
+constexpr int kPowPitch = 548;                   // floats per power row: >= 520 and == 4 (mod 32)
+constexpr int kMaxHopBulk = 256;                 // staging buffer holds 1024 + hop samples
+constexpr int kStageFloats = kN + kMaxHopBulk;
+constexpr int kMaxItems = 32;                    // k-chunks of filter groups per CTA iteration
+constexpr int kMaxItemsPerWarp = 16;
+constexpr int kFragSmemSteps = 112;              // filterbank fragments kept in shared memory (x 512 B)
+
+// The mel contraction D[16 frames][n_mels] = P[16][bins] * F[bins][n_mels] is cut into ITEMS:
+// (group of 8 filters) x (chunk of consecutive 8-bin k-steps where that group is non-zero).
+// Items are spread over the 8 warps by descending size; partial sums meet in shared memory and
+// are added in a fixed order, so results do not depend on scheduling.
+struct MelItem {
+  int tile;      // filter group: filters [8 tile, 8 tile + 8)
+  int kstart;    // first bin of the chunk (multiple of 8)
+  int nsteps;    // k-steps in the chunk
+  int frag_off;  // index of the chunk's first step in the fragment array
+};
+struct MelTile {
+  int part[4];  // item indices whose partial sums make up this filter group; kMaxItems == "all zero"
+};
+struct MelPlan {  // built on the device by prepare_mma_kernel
+  int n_tiles, n_items, total_steps, chunk;
+  int warp_cnt[kWarps];
+  int warp_items[kWarps][kMaxItemsPerWarp];
+  MelItem items[kMaxItems];
+  MelTile tiles[64];
+};
 
 struct Pow2Extra {  // tables appended to the generic workspace
-  size_t tw2d, csr_off, csr_lo, csr_w, total;
+  size_t tw2d, plan, frags, total;
 };
+
+inline int mel_tiles(int n_mels) { return (n_mels + 7) / 8; }
 
 inline Pow2Extra pow2_layout(const b200a_frontend_desc& d, size_t base) {
   Pow2Extra e{};
   const size_t n_bins = d.n_fft / 2 + 1;
-  const size_t n_mels = d.n_mels > 0 ? d.n_mels : 0;
+  const size_t nt = d.n_mels > 0 ? mel_tiles(d.n_mels) : 0;
   size_t off = base;
   e.tw2d = off;
   off = align_up(off + sizeof(float2) * 32 * 32, 256);
-  e.csr_off = off;
-  off = align_up(off + sizeof(int) * (n_mels + 1), 256);
-  e.csr_lo = off;
-  off = align_up(off + sizeof(int) * (n_mels + 1), 256);
-  e.csr_w = off;
-  off = align_up(off + sizeof(float) * n_bins * n_mels, 256);
+  e.plan = off;
+  off = align_up(off + sizeof(MelPlan), 256);
+  e.frags = off;  // worst case: every tile spans every bin
+  off = align_up(off + sizeof(float4) * 32 * nt * ((n_bins + 7) / 8 + 1), 256);
   e.total = off;
   return e;
 }
@@ -122,6 +161,45 @@ __device__ __forceinline__ void fft32(float2 (&a)[32]) {
   });
 }
 
+// ---- mbarrier / bulk-copy / mma PTX -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// Bounded wait: a mis-programmed copy traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (int spin = 0; spin < (1 << 24); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 struct Pow2Params {
   const float* wave;
   int64_t length, row_stride, frames, pairs_per_row, total_pairs;
@@ -130,48 +208,92 @@ struct Pow2Params {
   int64_t rows_per_group;
   const float* window;   // [1024] centre padded
   const float2* tw2d;    // [32][32]  W_1024^(k2 * g) at [k2][g]
-  const int* csr_off;    // [n_mels + 1]
-  const int* csr_lo;     // [n_mels]
-  const float* csr_w;    // compacted non-zero runs of the filterbank columns
+  const MelPlan* plan;
+  const float4* frags;   // [steps][32] (b0_hi, b1_hi, b0_lo, b1_lo) in mma B-fragment order
   const WsHeader* hdr;
   int hop, pad, center, pad_mode, n_mels;
-  int stage, log_mels;
+  int stage, log_mels, bulk_ok;
   float power, db_mult, db_amin, db_offset;
 };
 
-template <int POWER_MODE>  // 2: |.|^2, 1: |.|, 0: general exponent
+template <int POWER_MODE>  // 2: |.|^2, 0: general exponent (1 handled inside)
 __device__ __forceinline__ float pow_of(float re, float im, float power) {
   if constexpr (POWER_MODE == 2) return fmaf(re, re, im * im);
   const float mag = hypotf(re, im);
-  if constexpr (POWER_MODE == 1) return mag;
-  return powf(mag, power);
+  return power == 1.f ? mag : powf(mag, power);
 }
 
-template <int POWER_MODE>
+// Running maximum of the dB features per top_db group, flushed with as few atomics as possible.
+struct GroupMax {
+  float* dst;
+  int64_t group;
+  float value;
+  // Warp-collective (all 32 lanes call it together; `dst` is warp-uniform).
+  __device__ __forceinline__ void flush() {
+    if (dst == nullptr) return;
+    const int64_t g0 = __shfl_sync(0xffffffffu, group, 0);
+    if (__all_sync(0xffffffffu, group == g0)) {
+      const float mx = warp_max(value);
+      if ((threadIdx.x & 31) == 0 && g0 >= 0 && mx > -CUDART_INF_F) atomic_max_f32(dst + g0, mx);
+    } else if (group >= 0 && value > -CUDART_INF_F) {
+      atomic_max_f32(dst + group, value);
+    }
+    value = -CUDART_INF_F;
+  }
+  // Must be called by all 32 lanes together; `valid == false` lanes contribute nothing.
+  __device__ __forceinline__ void add(int64_t g, float v, bool valid) {
+    if (dst == nullptr) return;
+    if (!valid) {
+      g = group;
+      v = -CUDART_INF_F;
+    }
+    // warp-collective flush only when ANY lane changes group (keeps the shuffles converged)
+    if (__any_sync(0xffffffffu, g != group && group >= 0)) flush();
+    group = g;
+    value = fmaxf(value, v);
+  }
+};
+
+template <int POWER_MODE, bool MEL, int HG>  // HG = hop / 32 when the b frame is a 32-aligned shift, else -1
 __global__ void __launch_bounds__(kWarps * 32, 1) stft1024_kernel(const Pow2Params p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* s_tw = reinterpret_cast<float2*>(smem_raw);                 // [32][32]
-  float2* s_tile_all = s_tw + 32 * 32;                                // [kWarps][32 * 33]
-  int* s_off = reinterpret_cast<int*>(s_tile_all + kWarps * kTileFloat2);  // [n_mels + 1]
-  int* s_lo = s_off + (p.n_mels + 1);                                 // [n_mels]
-  float* s_w = reinterpret_cast<float*>(s_lo + p.n_mels + 1);         // [csr_total] (if it fits)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);                          // [32][32]
+  float2* s_tile_all = s_tw + 32 * 32;                                         // [kWarps][32 * 33]
+  float* s_stage_all = reinterpret_cast<float*>(s_tile_all + kWarps * kTileFloat2);  // [kWarps][kStageFloats]
+  float* s_pow = s_stage_all + kWarps * kStageFloats;                          // [kSlots][kPowPitch]      (MEL)
+  float* s_part = s_pow + (MEL ? kSlots * kPowPitch : 0);                      // [kMaxItems + 1][16][8]   (MEL)
+  int64_t* s_slot = reinterpret_cast<int64_t*>(s_part + (MEL ? (kMaxItems + 1) * 128 : 0));  // [2][kSlots] out offsets
+  int64_t* s_grp = s_slot + 2 * kSlots;                                        // [2][kSlots] top_db group
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + 2 * kSlots);           // [kWarps]
+  MelPlan* s_plan = reinterpret_cast<MelPlan*>(s_bar + kWarps);                // (MEL)
+  float4* s_frags = reinterpret_cast<float4*>(s_plan + 1);                     // [<= kFragSmemSteps][32] (MEL)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 32 * 32; i += blockDim.x) s_tw[i] = p.tw2d[i];
-  const bool mel_stage = p.stage >= B200A_STAGE_MEL;
-  const int csr_total = mel_stage ? p.csr_off[p.n_mels] : 0;
-  const bool w_in_smem = mel_stage && csr_total <= kCsrSmemMax;
-  if (mel_stage) {
-    for (int i = tid; i <= p.n_mels; i += blockDim.x) s_off[i] = p.csr_off[i];
-    for (int i = tid; i < p.n_mels; i += blockDim.x) s_lo[i] = p.csr_lo[i];
-    if (w_in_smem)
-      for (int i = tid; i < csr_total; i += blockDim.x) s_w[i] = p.csr_w[i];
+  bool frags_in_smem = false;
+  if constexpr (MEL) {
+    const int* src = reinterpret_cast<const int*>(p.plan);
+    int* dst = reinterpret_cast<int*>(s_plan);
+    for (int i = tid; i < (int)(sizeof(MelPlan) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    const int total_steps = p.plan->total_steps;
+    frags_in_smem = total_steps <= kFragSmemSteps;
+    if (frags_in_smem)
+      for (int i = tid; i < total_steps * 32; i += blockDim.x) s_frags[i] = p.frags[i];
+    // columns >= 513 of every power row are read by the last k-step: keep them finite (zero)
+    for (int i = tid; i < kSlots * (kPowPitch - kBins); i += blockDim.x) {
+      const int r = i / (kPowPitch - kBins), c = i - r * (kPowPitch - kBins);
+      s_pow[r * kPowPitch + kBins + c] = 0.f;
+    }
+    for (int i = tid; i < 128; i += blockDim.x) s_part[kMaxItems * 128 + i] = 0.f;  // the "no item" block
   }
+  const float4* __restrict__ frag_base = frags_in_smem ? s_frags : p.frags;
+  if (tid < kWarps) mbar_init(s_bar + tid, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  const float* __restrict__ fbw = w_in_smem ? s_w : p.csr_w;
 
   float2* tile = s_tile_all + warp * kTileFloat2;
-  float* ptile = reinterpret_cast<float*>(tile);  // power rows of frames a, b at 0 and kPowLd
+  float* stage = s_stage_all + warp * kStageFloats;
+  uint64_t* bar = s_bar + warp;
 
   // window (x 1/2 from the un-packing, x the normalisation scale) for n = lane + 32 j
   float wreg[32];
@@ -181,151 +303,251 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stft1024_kernel(const Pow2Para
     for (int j = 0; j < 32; ++j) wreg[j] = p.window[lane + 32 * j] * hs;
   }
   const int half = p.center ? kN / 2 : 0;
-  float local_max = -CUDART_INF_F;
-  int64_t cur_group = -1;
+  const int width = MEL ? p.n_mels : kBins;
+  const uint32_t bulk_bytes = (uint32_t)(kN + p.hop) * 4u;
+  uint32_t parity = 0;
+  bool staged = false;  // the pair of THIS iteration was prefetched into `stage`
+  GroupMax gmax{p.stage == B200A_STAGE_FEAT ? p.group_max : nullptr, -1, -CUDART_INF_F};
 
-  for (int64_t u = (int64_t)blockIdx.x * kWarps + warp; u < p.total_pairs; u += (int64_t)gridDim.x * kWarps) {
-    const int64_t row = u / p.pairs_per_row;
-    const int64_t pr = u - row * p.pairs_per_row;
-    const int64_t ta = 2 * pr, tb = ta + 1;
-    const bool has_b = tb < p.frames;
-    const float* __restrict__ x = p.wave + row * p.row_stride;
-    if (p.stage == B200A_STAGE_FEAT && p.group_max != nullptr) {
-      const int64_t grp = row / p.rows_per_group;
-      if (grp != cur_group) {  // flush the running maximum when the warp moves to another top_db group
-        const float mx = warp_max(local_max);
-        if (lane == 0 && cur_group >= 0 && mx > -CUDART_INF_F) atomic_max_f32(p.group_max + cur_group, mx);
-        local_max = -CUDART_INF_F;
-        cur_group = grp;
-      }
-    }
-    const int64_t sa = ta * p.hop - half - p.pad;  // first raw sample of frame a
-    const int64_t sb = sa + p.hop;
+  // (row, pair-in-row) of this warp's current and next pair, advanced without divisions
+  const int64_t stride = (int64_t)gridDim.x * kWarps;
+  const int64_t u0 = (int64_t)blockIdx.x * kWarps;
+  const int64_t step_rows = stride / p.pairs_per_row, step_pairs = stride - step_rows * p.pairs_per_row;
+  int64_t cur_row = (u0 + warp) / p.pairs_per_row, cur_pr = (u0 + warp) - cur_row * p.pairs_per_row;
+  int64_t nxt_row = cur_row + step_rows, nxt_pr = cur_pr + step_pairs;
+  if (nxt_pr >= p.pairs_per_row) { nxt_pr -= p.pairs_per_row; ++nxt_row; }
 
-    float2 a[32];
-    const bool interior = sa >= 0 && (has_b ? sb : sa) + kN <= p.length;
-    if (interior) {
-      static_for<32>([&](auto ji) {
-        constexpr int j = decltype(ji)::value;
-        const float va = __ldg(x + sa + lane + 32 * j);
-        const float vb = has_b ? __ldg(x + sb + lane + 32 * j) : 0.f;
-        a[brev5(j)] = make_float2(va * wreg[j], vb * wreg[j]);
-      });
-    } else {
-      // edge pair (padding / reflection / ragged end): gather through the warp's tile with a
-      // rolled loop so the index arithmetic is not replicated 64 times in the instruction stream
-#pragma unroll 1
-      for (int j = 0; j < 32; ++j) {
-        const int n = lane + 32 * j;
-        const int64_t ia = source_index(ta * p.hop + n, p.length, p.pad, half, p.pad_mode);
-        const int64_t ib = has_b ? source_index(tb * p.hop + n, p.length, p.pad, half, p.pad_mode) : -1;
-        tile[n] = make_float2(ia >= 0 ? __ldg(x + ia) : 0.f, ib >= 0 ? __ldg(x + ib) : 0.f);
-      }
-      __syncwarp();
-      static_for<32>([&](auto ji) {
-        constexpr int j = decltype(ji)::value;
-        const float2 v = tile[lane + 32 * j];
-        a[brev5(j)] = make_float2(v.x * wreg[j], v.y * wreg[j]);
-      });
-      __syncwarp();
-    }
+  // a pair can be staged by one bulk copy iff both frames exist and lie inside the row un-padded
+  auto bulk_eligible = [&](int64_t u, int64_t pr) -> bool {
+    if (!p.bulk_ok || u >= p.total_pairs) return false;
+    const int64_t sa = 2 * pr * p.hop - half - p.pad;
+    return 2 * pr + 1 < p.frames && sa >= 0 && sa + p.hop + kN <= p.length;
+  };
+  auto issue_bulk = [&](int64_t row, int64_t pr) {
+    const float* src = p.wave + row * p.row_stride + (2 * pr * p.hop - half - p.pad);
+    mbar_expect_tx(bar, bulk_bytes);
+    bulk_g2s(stage, src, bulk_bytes, bar);
+  };
 
-    fft32(a);  // a[k2] = Y[lane][k2]
+  if (bulk_eligible(u0 + warp, cur_pr)) {
+    if (lane == 0) issue_bulk(cur_row, cur_pr);
+    staged = true;
+  }
 
-    // twiddle + transpose: element (g = lane, k2) -> tile[k2][g]
-    tile[lane] = a[0];
-    static_for<31>([&](auto ki) {
-      constexpr int k2 = decltype(ki)::value + 1;
-      const float2 w = s_tw[k2 * 32 + lane];
-      const float2 v = a[k2];
-      tile[k2 * kTileLd + lane] = make_float2(fmaf(v.x, w.x, -v.y * w.y), fmaf(v.x, w.y, v.y * w.x));
-    });
-    __syncwarp();
-    static_for<32>([&](auto gi) {
-      constexpr int g = decltype(gi)::value;
-      a[brev5(g)] = tile[lane * kTileLd + g];
-    });
-    __syncwarp();
-
-    fft32(a);  // a[k1] = Z[lane + 32 k1]
-
-    // ---- un-pack the two spectra: need Z[N - k], k = lane + 32 k1, k1 = 0..15 (+ bin 512 on lane 0)
-    const int src = (32 - lane) & 31;
+  int buf = 0;
+  for (int64_t base = u0; base < p.total_pairs; base += stride, buf ^= 1) {
+    const int64_t u = base + warp;
+    const bool valid = u < p.total_pairs;
+    const int64_t row = cur_row, this_pr = cur_pr;
+    int64_t ta = 0;
+    bool has_b = false;
     float pa[17], pb[17];
-    static_for<16>([&](auto ki) {
-      constexpr int k1 = decltype(ki)::value;
-      // lanes >= 1: Z[N-k] = Z[(32-lane) + 32 (31-k1)] sits on lane `src`, slot 31-k1
-      float mr = __shfl_sync(0xffffffffu, a[31 - k1].x, src);
-      float mi = __shfl_sync(0xffffffffu, a[31 - k1].y, src);
-      if (lane == 0) {  // lane 0: Z[N-k] = Z[32 (32-k1)] is its own slot 32-k1 (slot 0 for k1 = 0)
-        mr = a[(32 - k1) & 31].x;
-        mi = a[(32 - k1) & 31].y;
-      }
-      const float zr = a[k1].x, zi = a[k1].y;
-      pa[k1] = pow_of<POWER_MODE>(zr + mr, zi - mi, p.power);
-      pb[k1] = pow_of<POWER_MODE>(zi + mi, mr - zr, p.power);
-    });
-    // bin 512 (lane 0, slot 16) is its own mirror: A = Re, B = Im  (x2 because wreg carries the 1/2)
-    pa[16] = pow_of<POWER_MODE>(2.f * a[16].x, 0.f, p.power);
-    pb[16] = pow_of<POWER_MODE>(2.f * a[16].y, 0.f, p.power);
 
-    if (p.stage == B200A_STAGE_POWER) {
-      float* oa = p.out + (row * p.frames + ta) * kBins;
-      float* ob = oa + kBins;
+    if (valid) {
+      const int64_t pr = this_pr;
+      ta = 2 * pr;
+      const int64_t tb = ta + 1;
+      has_b = tb < p.frames;
+      const float* __restrict__ x = p.wave + row * p.row_stride;
+      const int64_t sa = ta * p.hop - half - p.pad;  // first raw sample of frame a
+      const int64_t sb = sa + p.hop;
+
+      float2 a[32];
+      if (staged) {
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        if constexpr (HG >= 0) {
+          float v[32 + (HG >= 0 ? HG : 0)];
+          static_for<32 + (HG >= 0 ? HG : 0)>([&](auto ji) {
+            constexpr int j = decltype(ji)::value;
+            v[j] = stage[lane + 32 * j];
+          });
+          static_for<32>([&](auto ji) {
+            constexpr int j = decltype(ji)::value;
+            a[brev5(j)] = make_float2(v[j] * wreg[j], v[j + (HG >= 0 ? HG : 0)] * wreg[j]);
+          });
+        } else {
+          const float* sb_ptr = stage + p.hop;
+          static_for<32>([&](auto ji) {
+            constexpr int j = decltype(ji)::value;
+            a[brev5(j)] = make_float2(stage[lane + 32 * j] * wreg[j], sb_ptr[lane + 32 * j] * wreg[j]);
+          });
+        }
+        __syncwarp();  // every lane has consumed the staging buffer
+      } else if (sa >= 0 && (has_b ? sb : sa) + kN <= p.length) {
+        static_for<32>([&](auto ji) {
+          constexpr int j = decltype(ji)::value;
+          const float va = __ldg(x + sa + lane + 32 * j);
+          const float vb = has_b ? __ldg(x + sb + lane + 32 * j) : 0.f;
+          a[brev5(j)] = make_float2(va * wreg[j], vb * wreg[j]);
+        });
+      } else {
+        // edge pair (padding / reflection / ragged end): gather through the warp's tile with a
+        // rolled loop so the index arithmetic is not replicated 64 times in the instruction stream
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) {
+          const int n = lane + 32 * j;
+          const int64_t ia = source_index(ta * p.hop + n, p.length, p.pad, half, p.pad_mode);
+          const int64_t ib = has_b ? source_index(tb * p.hop + n, p.length, p.pad, half, p.pad_mode) : -1;
+          tile[n] = make_float2(ia >= 0 ? __ldg(x + ia) : 0.f, ib >= 0 ? __ldg(x + ib) : 0.f);
+        }
+        __syncwarp();
+        static_for<32>([&](auto ji) {
+          constexpr int j = decltype(ji)::value;
+          const float2 v = tile[lane + 32 * j];
+          a[brev5(j)] = make_float2(v.x * wreg[j], v.y * wreg[j]);
+        });
+        __syncwarp();
+      }
+      // prefetch the next pair of this warp; it lands while the FFT below runs
+      staged = bulk_eligible(u + stride, nxt_pr);
+      if (staged && lane == 0) issue_bulk(nxt_row, nxt_pr);
+
+      fft32(a);  // a[k2] = Y[lane][k2]
+
+      // twiddle + transpose: element (g = lane, k2) -> tile[k2][g]
+      tile[lane] = a[0];
+      static_for<31>([&](auto ki) {
+        constexpr int k2 = decltype(ki)::value + 1;
+        const float2 w = s_tw[k2 * 32 + lane];
+        const float2 v = a[k2];
+        tile[k2 * kTileLd + lane] = make_float2(fmaf(v.x, w.x, -v.y * w.y), fmaf(v.x, w.y, v.y * w.x));
+      });
+      __syncwarp();
+      static_for<32>([&](auto gi) {
+        constexpr int g = decltype(gi)::value;
+        a[brev5(g)] = tile[lane * kTileLd + g];
+      });
+      __syncwarp();
+
+      fft32(a);  // a[k1] = Z[lane + 32 k1]
+
+      // ---- un-pack the two spectra: need Z[N - k], k = lane + 32 k1, k1 = 0..15 (+ bin 512 on lane 0)
+      const int src = (32 - lane) & 31;
+      static_for<16>([&](auto ki) {
+        constexpr int k1 = decltype(ki)::value;
+        // lanes >= 1: Z[N-k] = Z[(32-lane) + 32 (31-k1)] sits on lane `src`, slot 31-k1
+        float mr = __shfl_sync(0xffffffffu, a[31 - k1].x, src);
+        float mi = __shfl_sync(0xffffffffu, a[31 - k1].y, src);
+        if (lane == 0) {  // lane 0: Z[N-k] = Z[32 (32-k1)] is its own slot 32-k1 (slot 0 for k1 = 0)
+          mr = a[(32 - k1) & 31].x;
+          mi = a[(32 - k1) & 31].y;
+        }
+        const float zr = a[k1].x, zi = a[k1].y;
+        pa[k1] = pow_of<POWER_MODE>(zr + mr, zi - mi, p.power);
+        pb[k1] = pow_of<POWER_MODE>(zi + mi, mr - zr, p.power);
+      });
+      // bin 512 (lane 0, slot 16) is its own mirror: A = Re, B = Im  (x2 because wreg carries the 1/2)
+      pa[16] = pow_of<POWER_MODE>(2.f * a[16].x, 0.f, p.power);
+      pb[16] = pow_of<POWER_MODE>(2.f * a[16].y, 0.f, p.power);
+    }
+
+    if constexpr (!MEL) {
+      if (valid) {
+        float* oa = p.out + (row * p.frames + ta) * kBins;
+        float* ob = oa + kBins;
 #pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) {
-        oa[lane + 32 * k1] = pa[k1];
-        if (has_b) ob[lane + 32 * k1] = pb[k1];
+        for (int k1 = 0; k1 < 16; ++k1) {
+          oa[lane + 32 * k1] = pa[k1];
+          if (has_b) ob[lane + 32 * k1] = pb[k1];
+        }
+        if (lane == 0) {
+          oa[512] = pa[16];
+          if (has_b) ob[512] = pb[16];
+        }
+      }
+    } else {
+      // ---- publish this warp's two power rows, then contract all 16 with the filterbank -------
+      const int sb_ = (buf & 1) * kSlots;  // slot bookkeeping is double buffered, the power tile is not
+      float* prow_a = s_pow + (size_t)(2 * warp) * kPowPitch;
+      float* prow_b = prow_a + kPowPitch;
+      if (valid) {
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) {
+          prow_a[lane + 32 * k1] = pa[k1];
+          prow_b[lane + 32 * k1] = pb[k1];
+        }
+        if (lane == 0) {
+          prow_a[512] = pa[16];
+          prow_b[512] = pb[16];
+        }
       }
       if (lane == 0) {
-        oa[512] = pa[16];
-        if (has_b) ob[512] = pb[16];
+        const int64_t oa = valid ? (row * p.frames + ta) * (int64_t)width : -1;
+        s_slot[sb_ + 2 * warp] = oa;
+        s_slot[sb_ + 2 * warp + 1] = (valid && has_b) ? oa + width : -1;
+        const int64_t g = row / p.rows_per_group;
+        s_grp[sb_ + 2 * warp] = g;
+        s_grp[sb_ + 2 * warp + 1] = g;
       }
-      continue;
-    }
+      __syncthreads();  // (1) all 16 power rows are in place
 
-    // ---- mel projection from the warp's shared power rows -------------------------------------
+      {  // this warp's items: partial D[16 x 8] = P[16 x chunk] * F[chunk x 8] on the tensor pipe
+        const int r = lane >> 2, c = lane & 3;
+        const int cnt = s_plan->warp_cnt[warp];
+        for (int ii = 0; ii < cnt; ++ii) {
+          const int item = s_plan->warp_items[warp][ii];
+          const MelItem mi = s_plan->items[item];
+          const float* a_lo_row = s_pow + (size_t)r * kPowPitch + mi.kstart + c;
+          const float* a_hi_row = a_lo_row + 8 * kPowPitch;
+          const float4* fr = frag_base + (size_t)mi.frag_off * 32 + lane;
+          // three independent accumulator chains (hi*hi, lo*hi, hi*lo), summed in a fixed order
+          float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+          for (int s = 0; s < mi.nsteps; ++s) {
+            const float4 b = fr[(size_t)s * 32];
+            float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
+            uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) {
-      ptile[lane + 32 * k1] = pa[k1];
-      ptile[kPowLd + lane + 32 * k1] = pb[k1];
-    }
-    if (lane == 0) {
-      ptile[512] = pa[16];
-      ptile[kPowLd + 512] = pb[16];
-    }
-    __syncwarp();
-    float* oa = p.out + (row * p.frames + ta) * p.n_mels;
-    for (int m = lane; m < p.n_mels; m += 32) {
-      const int off = s_off[m], len = s_off[m + 1] - off, lo = s_lo[m];
-      const float* ra = ptile + lo;
-      const float* rb = ra + kPowLd;
-      const float* w = fbw + off;
-      float acc_a = 0.f, acc_b = 0.f;
-      for (int i = 0; i < len; ++i) {
-        const float wv = w[i];
-        acc_a = fmaf(ra[i], wv, acc_a);
-        acc_b = fmaf(rb[i], wv, acc_b);
-      }
-      if (p.stage == B200A_STAGE_FEAT) {
-        if (p.log_mels) {
-          acc_a = logf(acc_a + 1e-6f);
-          acc_b = logf(acc_b + 1e-6f);
-        } else {
-          acc_a = p.db_mult * log10f(fmaxf(acc_a, p.db_amin)) - p.db_offset;
-          acc_b = p.db_mult * log10f(fmaxf(acc_b, p.db_amin)) - p.db_offset;
+            for (int q = 0; q < 4; ++q) {
+              hi[q] = __float_as_uint(av[q]) & 0xffffe000u;
+              lo[q] = __float_as_uint(av[q] - __uint_as_float(hi[q]));
+            }
+            mma_tf32(d0, hi, __float_as_uint(b.x), __float_as_uint(b.y));
+            mma_tf32(d1, lo, __float_as_uint(b.x), __float_as_uint(b.y));
+            mma_tf32(d2, hi, __float_as_uint(b.z), __float_as_uint(b.w));
+          }
+          float d[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d[q] = d0[q] + (d1[q] + d2[q]);
+          float2* dst = reinterpret_cast<float2*>(s_part + item * 128 + r * 8 + 2 * c);
+          dst[0] = make_float2(d[0], d[1]);
+          dst[32] = make_float2(d[2], d[3]);  // row r + 8
         }
-        local_max = fmaxf(local_max, has_b ? fmaxf(acc_a, acc_b) : acc_a);
       }
-      oa[m] = acc_a;
-      if (has_b) oa[p.n_mels + m] = acc_b;
+      __syncthreads();  // (2) all partial products are in place
+
+      {  // fixed-order sum of (up to 4) k-chunks, (dB / log), coalesced store: lane -> filter, warp pairs -> slots
+        for (int nb = 0; nb < p.n_mels; nb += 128) {
+          const int n = nb + (tid & 127);
+          const bool n_ok = n < p.n_mels;
+          const MelTile mt = s_plan->tiles[n_ok ? (n >> 3) : 0];
+          const float* p0 = s_part + mt.part[0] * 128 + (n & 7);
+          const float* p1 = s_part + mt.part[1] * 128 + (n & 7);
+          const float* p2 = s_part + mt.part[2] * 128 + (n & 7);
+          const float* p3 = s_part + mt.part[3] * 128 + (n & 7);
+#pragma unroll
+          for (int si = 0; si < kSlots / 2; ++si) {
+            const int slot = 2 * si + (tid >> 7);
+            float v = (p0[slot * 8] + p1[slot * 8]) + (p2[slot * 8] + p3[slot * 8]);
+            const int64_t dst = s_slot[sb_ + slot];
+            const bool live = n_ok && dst >= 0;
+            if (p.stage == B200A_STAGE_FEAT) {
+              v = p.log_mels ? logf(v + 1e-6f) : p.db_mult * log10f(fmaxf(v, p.db_amin)) - p.db_offset;
+              gmax.add(s_grp[sb_ + slot], v, live);
+            }
+            if (live) p.out[dst + n] = v;
+          }
+        }
+      }
     }
-    __syncwarp();
+    cur_row = nxt_row;
+    cur_pr = nxt_pr;
+    nxt_row += step_rows;
+    nxt_pr += step_pairs;
+    if (nxt_pr >= p.pairs_per_row) { nxt_pr -= p.pairs_per_row; ++nxt_row; }
   }
-  if (p.stage == B200A_STAGE_FEAT && p.group_max != nullptr && cur_group >= 0) {
-    const float mx = warp_max(local_max);
-    if (lane == 0 && mx > -CUDART_INF_F) atomic_max_f32(p.group_max + cur_group, mx);
-  }
+  gmax.flush();
 }
 
 // ---- table preparation ------------------------------------------------------------------------
@@ -339,26 +561,84 @@ __global__ void prepare_tw2d_kernel(float2* tw2d) {
   }
 }
 
-// Compacts the non-zero run of every filterbank column (bands found by prepare_fbank_kernel).
-__global__ void prepare_csr_kernel(const float* __restrict__ fb, const int2* __restrict__ bands, int n_bins, int n_mels,
-                                   int* csr_off, int* csr_lo, float* csr_w) {
-  __shared__ int s_total;
+// Builds the mel contraction plan: per group of 8 filters the 8-bin k-steps its non-zero bins span,
+// cut into chunks (items), spread over the warps by descending size; and the filterbank values split
+// into TF32 hi/lo parts in mma.m16n8k8 B-fragment order.
+__global__ void prepare_mma_kernel(const float* __restrict__ fb, const int2* __restrict__ bands, int n_bins, int n_mels,
+                                   int n_tiles, MelPlan* plan, float4* frags) {
+  __shared__ int t_kstart[64], t_steps[64];
   if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int m = 0; m < n_mels; ++m) {
-      csr_off[m] = acc;
-      csr_lo[m] = bands[m].x;
-      acc += bands[m].y - bands[m].x;
+    int total = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      int lo = n_bins, hi = 0;
+      for (int m = 8 * t; m < min(8 * t + 8, n_mels); ++m) {
+        const int2 b = bands[m];
+        if (b.y > b.x) { lo = min(lo, b.x); hi = max(hi, b.y); }
+      }
+      t_kstart[t] = hi > lo ? (lo & ~7) : 0;
+      t_steps[t] = hi > lo ? (hi - t_kstart[t] + 7) / 8 : 0;
+      total += t_steps[t];
     }
-    csr_off[n_mels] = acc;
-    s_total = acc;
+    // chunk length: aim at ~2-3 items per warp, never more than kMaxItems in total
+    int chunk = max(4, (total + 2 * kWarps - 1) / (2 * kWarps));
+    for (;;) {  // at most 4 chunks per group and kMaxItems chunks in total
+      int n = 0, worst = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int parts = (t_steps[t] + chunk - 1) / chunk;
+        n += parts;
+        worst = max(worst, parts);
+      }
+      if (n <= kMaxItems && worst <= 4) break;
+      ++chunk;
+    }
+    int n_items = 0, off = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int parts = (t_steps[t] + chunk - 1) / chunk;
+      for (int q = 0; q < 4; ++q) plan->tiles[t].part[q] = q < parts ? n_items + q : kMaxItems;
+      for (int q = 0; q < parts; ++q) {  // near-equal parts
+        const int b0 = (int)((long long)t_steps[t] * q / parts), b1 = (int)((long long)t_steps[t] * (q + 1) / parts);
+        plan->items[n_items++] = MelItem{t, t_kstart[t] + 8 * b0, b1 - b0, off + b0};
+      }
+      off += t_steps[t];
+    }
+    plan->n_tiles = n_tiles;
+    plan->n_items = n_items;
+    plan->total_steps = total;
+    plan->chunk = chunk;
+    // longest-processing-time-first assignment of items to warps
+    int load[kWarps];
+    bool used[kMaxItems];
+    for (int w = 0; w < kWarps; ++w) { load[w] = 0; plan->warp_cnt[w] = 0; }
+    for (int i = 0; i < n_items; ++i) used[i] = false;
+    for (int k = 0; k < n_items; ++k) {
+      int best = -1;
+      for (int i = 0; i < n_items; ++i)
+        if (!used[i] && (best < 0 || plan->items[i].nsteps > plan->items[best].nsteps)) best = i;
+      used[best] = true;
+      int w = 0;
+      for (int q = 1; q < kWarps; ++q)
+        if (load[q] < load[w] || (load[q] == load[w] && plan->warp_cnt[q] < plan->warp_cnt[w])) w = q;
+      if (plan->warp_cnt[w] >= kMaxItemsPerWarp) {  // cannot happen with kMaxItems <= 2 * kMaxItemsPerWarp
+        for (w = 0; plan->warp_cnt[w] >= kMaxItemsPerWarp; ++w) {}
+      }
+      plan->warp_items[w][plan->warp_cnt[w]++] = best;
+      load[w] += plan->items[best].nsteps;
+    }
   }
   __syncthreads();
-  (void)s_total;
-  for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
-    const int2 b = bands[m];
-    const int off = csr_off[m];
-    for (int k = b.x; k < b.y; ++k) csr_w[off + (k - b.x)] = fb[(size_t)k * n_mels + m];
+  int off = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    for (int i = threadIdx.x; i < t_steps[t] * 32; i += blockDim.x) {
+      const int s = i >> 5, lane = i & 31;
+      const int n = 8 * t + (lane >> 2);
+      const int k0 = t_kstart[t] + 8 * s + (lane & 3), k1 = k0 + 4;
+      const float b0 = (n < n_mels && k0 < n_bins) ? fb[(size_t)k0 * n_mels + n] : 0.f;
+      const float b1 = (n < n_mels && k1 < n_bins) ? fb[(size_t)k1 * n_mels + n] : 0.f;
+      const float b0h = __uint_as_float(__float_as_uint(b0) & 0xffffe000u);
+      const float b1h = __uint_as_float(__float_as_uint(b1) & 0xffffe000u);
+      frags[(size_t)(off + s) * 32 + lane] = make_float4(b0h, b1h, b0 - b0h, b1 - b1h);
+    }
+    off += t_steps[t];
   }
 }
 
@@ -377,29 +657,53 @@ int pow2_prepare(const b200a_frontend_desc* d, void* ws, size_t ws_bytes, cudaSt
   if (ws_bytes < e.total) return B200A_EWORKSPACE;
   unsigned char* base = static_cast<unsigned char*>(ws);
   prepare_tw2d_kernel<<<4, 256, 0, stream>>>(reinterpret_cast<float2*>(base + e.tw2d));
-  if (d->n_mels > 0) {
-    prepare_csr_kernel<<<1, 128, 0, stream>>>(reinterpret_cast<const float*>(base + l.fb),
+  if (d->n_mels > 0 && mel_tiles(d->n_mels) <= 64) {
+    prepare_mma_kernel<<<1, 256, 0, stream>>>(reinterpret_cast<const float*>(base + l.fb),
                                               reinterpret_cast<const int2*>(base + l.bands), d->n_fft / 2 + 1, d->n_mels,
-                                              reinterpret_cast<int*>(base + e.csr_off),
-                                              reinterpret_cast<int*>(base + e.csr_lo),
-                                              reinterpret_cast<float*>(base + e.csr_w));
+                                              mel_tiles(d->n_mels), reinterpret_cast<MelPlan*>(base + e.plan),
+                                              reinterpret_cast<float4*>(base + e.frags));
   }
   return launch_status();
 }
 
-template <int POWER_MODE>
-static int launch_1024(const Pow2Params& p, size_t smem, int64_t grid, cudaStream_t stream) {
-  if (cudaFuncSetAttribute(stft1024_kernel<POWER_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
-      cudaSuccess)
+template <int POWER_MODE, bool MEL, int HG>
+static int launch_1024(const Pow2Params& p, cudaStream_t stream) {
+  size_t smem = sizeof(float2) * (32 * 32 + kWarps * kTileFloat2) + sizeof(float) * kWarps * kStageFloats +
+                sizeof(int64_t) * 4 * kSlots + sizeof(uint64_t) * kWarps;
+  if (MEL)
+    smem += sizeof(float) * (kSlots * kPowPitch + (kMaxItems + 1) * 128) + sizeof(MelPlan) +
+            sizeof(float4) * 32 * kFragSmemSteps;
+  static_assert(sizeof(MelPlan) % 16 == 0, "fragment array must stay 16-byte aligned");
+  if (smem > 227 * 1024) return B200A_EUNSUPPORTED;
+  auto kern = stft1024_kernel<POWER_MODE, MEL, HG>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return B200A_ECUDA;
-  stft1024_kernel<POWER_MODE><<<(unsigned)grid, kWarps * 32, smem, stream>>>(p);
+  // persistent: one resident CTA per SM, pairs dealt round-robin (every CTA gets the same count +-1)
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return B200A_ECUDA;
+    num_sms = n > 0 ? n : 148;
+  }
+  const int64_t iters = (p.total_pairs + kWarps - 1) / kWarps;
+  int64_t grid = iters < num_sms ? iters : num_sms;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(p);
   return launch_status();
+}
+
+template <int POWER_MODE, bool MEL>
+static int launch_hg(const Pow2Params& p, cudaStream_t stream) {
+  if (p.bulk_ok && p.hop == 256) return launch_1024<POWER_MODE, MEL, 8>(p, stream);
+  return launch_1024<POWER_MODE, MEL, -1>(p, stream);
 }
 
 int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, const float* wave, int64_t rows,
                       int64_t length, int64_t row_stride, int64_t frames, float* out, float* group_max,
                       int64_t rows_per_group, cudaStream_t stream) {
   if (!pow2_applicable(*d) || stage == B200A_STAGE_COMPLEX) return B200A_EUNSUPPORTED;
+  if (stage >= B200A_STAGE_MEL && mel_tiles(d->n_mels) > 64) return B200A_EUNSUPPORTED;  // > 512 filters: generic path
   const WsLayout l = ws_layout(*d);
   const Pow2Extra e = pow2_layout(*d, l.total);
   const unsigned char* base = static_cast<const unsigned char*>(ws);
@@ -415,9 +719,8 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
   p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
   p.window = reinterpret_cast<const float*>(base + l.window);
   p.tw2d = reinterpret_cast<const float2*>(base + e.tw2d);
-  p.csr_off = reinterpret_cast<const int*>(base + e.csr_off);
-  p.csr_lo = reinterpret_cast<const int*>(base + e.csr_lo);
-  p.csr_w = reinterpret_cast<const float*>(base + e.csr_w);
+  p.plan = reinterpret_cast<const MelPlan*>(base + e.plan);
+  p.frags = reinterpret_cast<const float4*>(base + e.frags);
   p.hdr = reinterpret_cast<const WsHeader*>(base + l.header);
   p.hop = d->hop;
   p.pad = d->pad;
@@ -430,15 +733,13 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
   p.db_mult = d->db_multiplier;
   p.db_amin = d->db_amin;
   p.db_offset = d->db_offset;
-  (void)kBins;
-  const size_t smem = sizeof(float2) * (32 * 32 + kWarps * kTileFloat2) + sizeof(int) * (2 * (size_t)d->n_mels + 4) +
-                      sizeof(float) * kCsrSmemMax;
-  int64_t grid = (p.total_pairs + kWarps - 1) / kWarps;
-  if (grid > 148 * 64) grid = 148 * 64;
-  if (grid < 1) grid = 1;
-  if (d->power == 2.f) return launch_1024<2>(p, smem, grid, stream);
-  if (d->power == 1.f) return launch_1024<1>(p, smem, grid, stream);
-  return launch_1024<0>(p, smem, grid, stream);
+  // bulk staging needs 16-byte aligned sources and sizes: every pair starts at 2*pr*hop - half - pad
+  const int half = d->center ? kN / 2 : 0;
+  p.bulk_ok = d->hop <= kMaxHopBulk && d->hop % 4 == 0 && (half + d->pad) % 4 == 0 && row_stride % 4 == 0 &&
+              (reinterpret_cast<uintptr_t>(wave) & 15) == 0;
+  const bool mel = stage >= B200A_STAGE_MEL;
+  if (d->power == 2.f) return mel ? launch_hg<2, true>(p, stream) : launch_hg<2, false>(p, stream);
+  return mel ? launch_hg<0, true>(p, stream) : launch_hg<0, false>(p, stream);
 }
 
 }  // namespace b200a
