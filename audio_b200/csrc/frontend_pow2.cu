@@ -43,8 +43,8 @@ constexpr int kTileFloat2 = 32 * kTileLd;        // per warp
 constexpr int kPowPitch = 548;                   // floats per power row: >= 520 and == 4 (mod 32)
 constexpr int kMaxHopBulk = 256;                 // staging buffer holds 1024 + hop samples
 constexpr int kStageFloats = kN + kMaxHopBulk;
-constexpr int kMaxItems = 32;                    // k-chunks of filter groups per CTA iteration
-constexpr int kMaxItemsPerWarp = 16;
+constexpr int kMaxItems = 64;                    // filter groups (of 8) per contraction
+constexpr int kMaxItemsPerWarp = 32;
 constexpr int kFragSmemSteps = 112;              // filterbank fragments kept in shared memory (x 512 B)
 
 // The mel contraction D[16 frames][n_mels] = P[16][bins] * F[bins][n_mels] is cut into ITEMS:
@@ -254,39 +254,196 @@ struct GroupMax {
   }
 };
 
-template <int POWER_MODE, bool MEL, int HG>  // HG = hop / 32 when the b frame is a 32-aligned shift, else -1
-__global__ void __launch_bounds__(kWarps * 32, 1) stft1024_kernel(const Pow2Params p) {
+// ---- mbarrier arrive (release, CTA scope) --------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// Per-warp walker over this warp's pairs: (row, pair-in-row) of the current and the next pair,
+// advanced without divisions.
+struct PairCursor {
+  int64_t u, stride, step_rows, step_pairs, ppr;
+  int64_t row, pr, nrow, npr;
+  __device__ __forceinline__ void init(int64_t first, int64_t stride_, int64_t pairs_per_row) {
+    u = first;
+    stride = stride_;
+    ppr = pairs_per_row;
+    step_rows = stride / ppr;
+    step_pairs = stride - step_rows * ppr;
+    row = first / ppr;
+    pr = first - row * ppr;
+    nrow = row + step_rows;
+    npr = pr + step_pairs;
+    if (npr >= ppr) { npr -= ppr; ++nrow; }
+  }
+  __device__ __forceinline__ void advance() {
+    u += stride;
+    row = nrow;
+    pr = npr;
+    nrow += step_rows;
+    npr += step_pairs;
+    if (npr >= ppr) { npr -= ppr; ++nrow; }
+  }
+};
+
+// a pair can be staged by one bulk copy iff both frames exist and lie inside the row un-padded
+__device__ __forceinline__ bool bulk_eligible(const Pow2Params& p, int half, int64_t u, int64_t pr) {
+  if (!p.bulk_ok || u >= p.total_pairs) return false;
+  const int64_t sa = 2 * pr * p.hop - half - p.pad;
+  return 2 * pr + 1 < p.frames && sa >= 0 && sa + p.hop + kN <= p.length;
+}
+__device__ __forceinline__ void issue_bulk(const Pow2Params& p, int half, int64_t row, int64_t pr, void* dst,
+                                           uint64_t* bar) {
+  const float* src = p.wave + row * p.row_stride + (2 * pr * p.hop - half - p.pad);
+  const uint32_t bytes = (uint32_t)(kN + p.hop) * 4u;
+  mbar_expect_tx(bar, bytes);
+  bulk_g2s(dst, src, bytes, bar);
+}
+
+// One warp, one pair of frames: samples -> windowed complex signal -> 1024-point FFT -> the two power
+// spectra.  On return lane l holds bins k = l + 32 k1 in pa[k1] / pb[k1] (k1 < 16) and lane 0 bin 512 in [16].
+//   stage      where a prefetched pair was staged (may alias `tile` when STAGE_IS_TILE)
+//   STAGE_IS_TILE  the staging buffer is the transpose tile itself: the NEXT pair's bulk copy is issued
+//                  only after pass 2 has read the tile back
+template <int POWER_MODE, int HG, bool STAGE_IS_TILE>
+__device__ __forceinline__ void transform_pair(const Pow2Params& p, const float (&wreg)[32], const float2* s_tw,
+                                               float2* tile, float* stage, uint64_t* bar, uint32_t& parity,
+                                               bool& staged, const PairCursor& cur, int half, int lane,
+                                               float (&pa)[17], float (&pb)[17]) {
+  const int64_t row = cur.row, ta = 2 * cur.pr, tb = ta + 1;
+  const bool has_b = tb < p.frames;
+  const float* __restrict__ x = p.wave + row * p.row_stride;
+  const int64_t sa = ta * p.hop - half - p.pad;  // first raw sample of frame a
+  const int64_t sb = sa + p.hop;
+  const bool next_staged = bulk_eligible(p, half, cur.u + cur.stride, cur.npr);
+
+  float2 a[32];
+  if (staged) {
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    if constexpr (HG >= 0) {
+      constexpr int kV = 32 + (HG >= 0 ? HG : 0);
+      float v[kV];
+      static_for<kV>([&](auto ji) {
+        constexpr int j = decltype(ji)::value;
+        v[j] = stage[lane + 32 * j];
+      });
+      static_for<32>([&](auto ji) {
+        constexpr int j = decltype(ji)::value;
+        a[brev5(j)] = make_float2(v[j] * wreg[j], v[j + (HG >= 0 ? HG : 0)] * wreg[j]);
+      });
+    } else {
+      const float* sb_ptr = stage + p.hop;
+      static_for<32>([&](auto ji) {
+        constexpr int j = decltype(ji)::value;
+        a[brev5(j)] = make_float2(stage[lane + 32 * j] * wreg[j], sb_ptr[lane + 32 * j] * wreg[j]);
+      });
+    }
+    __syncwarp();  // every lane has consumed the staging buffer
+  } else if (sa >= 0 && (has_b ? sb : sa) + kN <= p.length) {
+    static_for<32>([&](auto ji) {
+      constexpr int j = decltype(ji)::value;
+      const float va = __ldg(x + sa + lane + 32 * j);
+      const float vb = has_b ? __ldg(x + sb + lane + 32 * j) : 0.f;
+      a[brev5(j)] = make_float2(va * wreg[j], vb * wreg[j]);
+    });
+  } else {
+    // edge pair (padding / reflection / ragged end): gather through the warp's tile with a
+    // rolled loop so the index arithmetic is not replicated 64 times in the instruction stream
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) {
+      const int n = lane + 32 * j;
+      const int64_t ia = source_index(ta * p.hop + n, p.length, p.pad, half, p.pad_mode);
+      const int64_t ib = has_b ? source_index(tb * p.hop + n, p.length, p.pad, half, p.pad_mode) : -1;
+      tile[n] = make_float2(ia >= 0 ? __ldg(x + ia) : 0.f, ib >= 0 ? __ldg(x + ib) : 0.f);
+    }
+    __syncwarp();
+    static_for<32>([&](auto ji) {
+      constexpr int j = decltype(ji)::value;
+      const float2 v = tile[lane + 32 * j];
+      a[brev5(j)] = make_float2(v.x * wreg[j], v.y * wreg[j]);
+    });
+    __syncwarp();
+  }
+  if constexpr (!STAGE_IS_TILE) {  // separate staging buffer: prefetch right away
+    staged = next_staged;
+    if (staged && lane == 0) issue_bulk(p, half, cur.nrow, cur.npr, stage, bar);
+  }
+
+  fft32(a);  // a[k2] = Y[lane][k2]
+
+  // twiddle + transpose: element (g = lane, k2) -> tile[k2][g]
+  tile[lane] = a[0];
+  static_for<31>([&](auto ki) {
+    constexpr int k2 = decltype(ki)::value + 1;
+    const float2 w = s_tw[k2 * 32 + lane];
+    const float2 v = a[k2];
+    tile[k2 * kTileLd + lane] = make_float2(fmaf(v.x, w.x, -v.y * w.y), fmaf(v.x, w.y, v.y * w.x));
+  });
+  __syncwarp();
+  static_for<32>([&](auto gi) {
+    constexpr int g = decltype(gi)::value;
+    a[brev5(g)] = tile[lane * kTileLd + g];
+  });
+  __syncwarp();
+  if constexpr (STAGE_IS_TILE) {  // the tile is free until the next pair's transpose: stage into it
+    staged = next_staged;
+    if (staged && lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads above -> async write
+      issue_bulk(p, half, cur.nrow, cur.npr, stage, bar);
+    }
+  }
+
+  fft32(a);  // a[k1] = Z[lane + 32 k1]
+
+  // ---- un-pack the two spectra: need Z[N - k], k = lane + 32 k1, k1 = 0..15 (+ bin 512 on lane 0)
+  const int src = (32 - lane) & 31;
+  static_for<16>([&](auto ki) {
+    constexpr int k1 = decltype(ki)::value;
+    // lanes >= 1: Z[N-k] = Z[(32-lane) + 32 (31-k1)] sits on lane `src`, slot 31-k1
+    float mr = __shfl_sync(0xffffffffu, a[31 - k1].x, src);
+    float mi = __shfl_sync(0xffffffffu, a[31 - k1].y, src);
+    if (lane == 0) {  // lane 0: Z[N-k] = Z[32 (32-k1)] is its own slot 32-k1 (slot 0 for k1 = 0)
+      mr = a[(32 - k1) & 31].x;
+      mi = a[(32 - k1) & 31].y;
+    }
+    const float zr = a[k1].x, zi = a[k1].y;
+    pa[k1] = pow_of<POWER_MODE>(zr + mr, zi - mi, p.power);
+    pb[k1] = pow_of<POWER_MODE>(zi + mi, mr - zr, p.power);
+  });
+  // bin 512 (lane 0, slot 16) is its own mirror: A = Re, B = Im  (x2 because wreg carries the 1/2)
+  pa[16] = pow_of<POWER_MODE>(2.f * a[16].x, 0.f, p.power);
+  pb[16] = pow_of<POWER_MODE>(2.f * a[16].y, 0.f, p.power);
+}
+
+__device__ __forceinline__ void load_window(const Pow2Params& p, int lane, float (&wreg)[32]) {
+  // window (x 1/2 from the un-packing, x the normalisation scale) for n = lane + 32 j
+  const float hs = 0.5f * p.hdr->scale;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) wreg[j] = p.window[lane + 32 * j] * hs;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Spectrogram kernel: 8 independent warps, power spectra straight to global memory.
+// ------------------------------------------------------------------------------------------------
+template <int POWER_MODE, int HG>
+__global__ void __launch_bounds__(kWarps * 32, 1) stft1024_power_kernel(const Pow2Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2* s_tw = reinterpret_cast<float2*>(smem_raw);                          // [32][32]
-  float2* s_tile_all = s_tw + 32 * 32;                                         // [kWarps][32 * 33]
-  float* s_stage_all = reinterpret_cast<float*>(s_tile_all + kWarps * kTileFloat2);  // [kWarps][kStageFloats]
-  float* s_pow = s_stage_all + kWarps * kStageFloats;                          // [kSlots][kPowPitch]      (MEL)
-  float* s_part = s_pow + (MEL ? kSlots * kPowPitch : 0);                      // [kMaxItems + 1][16][8]   (MEL)
-  int64_t* s_slot = reinterpret_cast<int64_t*>(s_part + (MEL ? (kMaxItems + 1) * 128 : 0));  // [2][kSlots] out offsets
-  int64_t* s_grp = s_slot + 2 * kSlots;                                        // [2][kSlots] top_db group
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + 2 * kSlots);           // [kWarps]
-  MelPlan* s_plan = reinterpret_cast<MelPlan*>(s_bar + kWarps);                // (MEL)
-  float4* s_frags = reinterpret_cast<float4*>(s_plan + 1);                     // [<= kFragSmemSteps][32] (MEL)
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);                                 // [32][32]
+  float2* s_tile_all = s_tw + 32 * 32;                                                // [kWarps][32 * 33]
+  float* s_stage_all = reinterpret_cast<float*>(s_tile_all + kWarps * kTileFloat2);   // [kWarps][kStageFloats]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage_all + kWarps * kStageFloats);  // [kWarps]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 32 * 32; i += blockDim.x) s_tw[i] = p.tw2d[i];
-  bool frags_in_smem = false;
-  if constexpr (MEL) {
-    const int* src = reinterpret_cast<const int*>(p.plan);
-    int* dst = reinterpret_cast<int*>(s_plan);
-    for (int i = tid; i < (int)(sizeof(MelPlan) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
-    const int total_steps = p.plan->total_steps;
-    frags_in_smem = total_steps <= kFragSmemSteps;
-    if (frags_in_smem)
-      for (int i = tid; i < total_steps * 32; i += blockDim.x) s_frags[i] = p.frags[i];
-    // columns >= 513 of every power row are read by the last k-step: keep them finite (zero)
-    for (int i = tid; i < kSlots * (kPowPitch - kBins); i += blockDim.x) {
-      const int r = i / (kPowPitch - kBins), c = i - r * (kPowPitch - kBins);
-      s_pow[r * kPowPitch + kBins + c] = 0.f;
-    }
-    for (int i = tid; i < 128; i += blockDim.x) s_part[kMaxItems * 128 + i] = 0.f;  // the "no item" block
-  }
-  const float4* __restrict__ frag_base = frags_in_smem ? s_frags : p.frags;
   if (tid < kWarps) mbar_init(s_bar + tid, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -294,172 +451,115 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stft1024_kernel(const Pow2Para
   float2* tile = s_tile_all + warp * kTileFloat2;
   float* stage = s_stage_all + warp * kStageFloats;
   uint64_t* bar = s_bar + warp;
-
-  // window (x 1/2 from the un-packing, x the normalisation scale) for n = lane + 32 j
   float wreg[32];
-  {
-    const float hs = 0.5f * p.hdr->scale;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) wreg[j] = p.window[lane + 32 * j] * hs;
-  }
+  load_window(p, lane, wreg);
   const int half = p.center ? kN / 2 : 0;
-  const int width = MEL ? p.n_mels : kBins;
-  const uint32_t bulk_bytes = (uint32_t)(kN + p.hop) * 4u;
   uint32_t parity = 0;
-  bool staged = false;  // the pair of THIS iteration was prefetched into `stage`
-  GroupMax gmax{p.stage == B200A_STAGE_FEAT ? p.group_max : nullptr, -1, -CUDART_INF_F};
-
-  // (row, pair-in-row) of this warp's current and next pair, advanced without divisions
-  const int64_t stride = (int64_t)gridDim.x * kWarps;
-  const int64_t u0 = (int64_t)blockIdx.x * kWarps;
-  const int64_t step_rows = stride / p.pairs_per_row, step_pairs = stride - step_rows * p.pairs_per_row;
-  int64_t cur_row = (u0 + warp) / p.pairs_per_row, cur_pr = (u0 + warp) - cur_row * p.pairs_per_row;
-  int64_t nxt_row = cur_row + step_rows, nxt_pr = cur_pr + step_pairs;
-  if (nxt_pr >= p.pairs_per_row) { nxt_pr -= p.pairs_per_row; ++nxt_row; }
-
-  // a pair can be staged by one bulk copy iff both frames exist and lie inside the row un-padded
-  auto bulk_eligible = [&](int64_t u, int64_t pr) -> bool {
-    if (!p.bulk_ok || u >= p.total_pairs) return false;
-    const int64_t sa = 2 * pr * p.hop - half - p.pad;
-    return 2 * pr + 1 < p.frames && sa >= 0 && sa + p.hop + kN <= p.length;
-  };
-  auto issue_bulk = [&](int64_t row, int64_t pr) {
-    const float* src = p.wave + row * p.row_stride + (2 * pr * p.hop - half - p.pad);
-    mbar_expect_tx(bar, bulk_bytes);
-    bulk_g2s(stage, src, bulk_bytes, bar);
-  };
-
-  if (bulk_eligible(u0 + warp, cur_pr)) {
-    if (lane == 0) issue_bulk(cur_row, cur_pr);
+  bool staged = false;
+  PairCursor cur;
+  cur.init((int64_t)blockIdx.x * kWarps + warp, (int64_t)gridDim.x * kWarps, p.pairs_per_row);
+  if (bulk_eligible(p, half, cur.u, cur.pr)) {
+    if (lane == 0) issue_bulk(p, half, cur.row, cur.pr, stage, bar);
     staged = true;
   }
-
-  int buf = 0;
-  for (int64_t base = u0; base < p.total_pairs; base += stride, buf ^= 1) {
-    const int64_t u = base + warp;
-    const bool valid = u < p.total_pairs;
-    const int64_t row = cur_row, this_pr = cur_pr;
-    int64_t ta = 0;
-    bool has_b = false;
+  for (; cur.u < p.total_pairs; cur.advance()) {
     float pa[17], pb[17];
-
-    if (valid) {
-      const int64_t pr = this_pr;
-      ta = 2 * pr;
-      const int64_t tb = ta + 1;
-      has_b = tb < p.frames;
-      const float* __restrict__ x = p.wave + row * p.row_stride;
-      const int64_t sa = ta * p.hop - half - p.pad;  // first raw sample of frame a
-      const int64_t sb = sa + p.hop;
-
-      float2 a[32];
-      if (staged) {
-        mbar_wait(bar, parity);
-        parity ^= 1;
-        if constexpr (HG >= 0) {
-          float v[32 + (HG >= 0 ? HG : 0)];
-          static_for<32 + (HG >= 0 ? HG : 0)>([&](auto ji) {
-            constexpr int j = decltype(ji)::value;
-            v[j] = stage[lane + 32 * j];
-          });
-          static_for<32>([&](auto ji) {
-            constexpr int j = decltype(ji)::value;
-            a[brev5(j)] = make_float2(v[j] * wreg[j], v[j + (HG >= 0 ? HG : 0)] * wreg[j]);
-          });
-        } else {
-          const float* sb_ptr = stage + p.hop;
-          static_for<32>([&](auto ji) {
-            constexpr int j = decltype(ji)::value;
-            a[brev5(j)] = make_float2(stage[lane + 32 * j] * wreg[j], sb_ptr[lane + 32 * j] * wreg[j]);
-          });
-        }
-        __syncwarp();  // every lane has consumed the staging buffer
-      } else if (sa >= 0 && (has_b ? sb : sa) + kN <= p.length) {
-        static_for<32>([&](auto ji) {
-          constexpr int j = decltype(ji)::value;
-          const float va = __ldg(x + sa + lane + 32 * j);
-          const float vb = has_b ? __ldg(x + sb + lane + 32 * j) : 0.f;
-          a[brev5(j)] = make_float2(va * wreg[j], vb * wreg[j]);
-        });
-      } else {
-        // edge pair (padding / reflection / ragged end): gather through the warp's tile with a
-        // rolled loop so the index arithmetic is not replicated 64 times in the instruction stream
-#pragma unroll 1
-        for (int j = 0; j < 32; ++j) {
-          const int n = lane + 32 * j;
-          const int64_t ia = source_index(ta * p.hop + n, p.length, p.pad, half, p.pad_mode);
-          const int64_t ib = has_b ? source_index(tb * p.hop + n, p.length, p.pad, half, p.pad_mode) : -1;
-          tile[n] = make_float2(ia >= 0 ? __ldg(x + ia) : 0.f, ib >= 0 ? __ldg(x + ib) : 0.f);
-        }
-        __syncwarp();
-        static_for<32>([&](auto ji) {
-          constexpr int j = decltype(ji)::value;
-          const float2 v = tile[lane + 32 * j];
-          a[brev5(j)] = make_float2(v.x * wreg[j], v.y * wreg[j]);
-        });
-        __syncwarp();
-      }
-      // prefetch the next pair of this warp; it lands while the FFT below runs
-      staged = bulk_eligible(u + stride, nxt_pr);
-      if (staged && lane == 0) issue_bulk(nxt_row, nxt_pr);
-
-      fft32(a);  // a[k2] = Y[lane][k2]
-
-      // twiddle + transpose: element (g = lane, k2) -> tile[k2][g]
-      tile[lane] = a[0];
-      static_for<31>([&](auto ki) {
-        constexpr int k2 = decltype(ki)::value + 1;
-        const float2 w = s_tw[k2 * 32 + lane];
-        const float2 v = a[k2];
-        tile[k2 * kTileLd + lane] = make_float2(fmaf(v.x, w.x, -v.y * w.y), fmaf(v.x, w.y, v.y * w.x));
-      });
-      __syncwarp();
-      static_for<32>([&](auto gi) {
-        constexpr int g = decltype(gi)::value;
-        a[brev5(g)] = tile[lane * kTileLd + g];
-      });
-      __syncwarp();
-
-      fft32(a);  // a[k1] = Z[lane + 32 k1]
-
-      // ---- un-pack the two spectra: need Z[N - k], k = lane + 32 k1, k1 = 0..15 (+ bin 512 on lane 0)
-      const int src = (32 - lane) & 31;
-      static_for<16>([&](auto ki) {
-        constexpr int k1 = decltype(ki)::value;
-        // lanes >= 1: Z[N-k] = Z[(32-lane) + 32 (31-k1)] sits on lane `src`, slot 31-k1
-        float mr = __shfl_sync(0xffffffffu, a[31 - k1].x, src);
-        float mi = __shfl_sync(0xffffffffu, a[31 - k1].y, src);
-        if (lane == 0) {  // lane 0: Z[N-k] = Z[32 (32-k1)] is its own slot 32-k1 (slot 0 for k1 = 0)
-          mr = a[(32 - k1) & 31].x;
-          mi = a[(32 - k1) & 31].y;
-        }
-        const float zr = a[k1].x, zi = a[k1].y;
-        pa[k1] = pow_of<POWER_MODE>(zr + mr, zi - mi, p.power);
-        pb[k1] = pow_of<POWER_MODE>(zi + mi, mr - zr, p.power);
-      });
-      // bin 512 (lane 0, slot 16) is its own mirror: A = Re, B = Im  (x2 because wreg carries the 1/2)
-      pa[16] = pow_of<POWER_MODE>(2.f * a[16].x, 0.f, p.power);
-      pb[16] = pow_of<POWER_MODE>(2.f * a[16].y, 0.f, p.power);
-    }
-
-    if constexpr (!MEL) {
-      if (valid) {
-        float* oa = p.out + (row * p.frames + ta) * kBins;
-        float* ob = oa + kBins;
+    transform_pair<POWER_MODE, HG, false>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa, pb);
+    const int64_t ta = 2 * cur.pr;
+    const bool has_b = ta + 1 < p.frames;
+    float* oa = p.out + (cur.row * p.frames + ta) * kBins;
+    float* ob = oa + kBins;
 #pragma unroll
-        for (int k1 = 0; k1 < 16; ++k1) {
-          oa[lane + 32 * k1] = pa[k1];
-          if (has_b) ob[lane + 32 * k1] = pb[k1];
-        }
-        if (lane == 0) {
-          oa[512] = pa[16];
-          if (has_b) ob[512] = pb[16];
-        }
-      }
-    } else {
-      // ---- publish this warp's two power rows, then contract all 16 with the filterbank -------
-      const int sb_ = (buf & 1) * kSlots;  // slot bookkeeping is double buffered, the power tile is not
-      float* prow_a = s_pow + (size_t)(2 * warp) * kPowPitch;
+    for (int k1 = 0; k1 < 16; ++k1) {
+      oa[lane + 32 * k1] = pa[k1];
+      if (has_b) ob[lane + 32 * k1] = pb[k1];
+    }
+    if (lane == 0) {
+      oa[512] = pa[16];
+      if (has_b) ob[512] = pb[16];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mel / MFCC-feature kernel, warp specialised: warps 0-7 transform (one frame pair each per iteration)
+// and publish power rows into a double-buffered shared tile; warps 8-11 contract each finished tile of
+// 16 frames with the filterbank on the tensor pipe and store the features.  The two groups only meet at
+// the tile's full/empty mbarriers, so the FFT warps never wait for the contraction.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMelWarps = 4;
+constexpr int kFftRegs = 216, kMelRegs = 64;  // 256*216 + 128*64 = 63488 <= 64512 = 384 * 168
+
+template <int POWER_MODE, int HG>
+__global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft1024_mel_kernel(const Pow2Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);                          // [32][32]
+  float2* s_tile_all = s_tw + 32 * 32;                                         // [kWarps][32 * 33] (also staging)
+  float* s_pow = reinterpret_cast<float*>(s_tile_all + kWarps * kTileFloat2);  // [2][kSlots][kPowPitch]
+  int64_t* s_slot = reinterpret_cast<int64_t*>(s_pow + 2 * kSlots * kPowPitch);  // [2][kSlots] out offsets
+  int64_t* s_grp = s_slot + 2 * kSlots;                                        // [2][kSlots] top_db group
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + 2 * kSlots);           // [kWarps] staging, [2] full, [2] empty
+  uint64_t* s_full = s_bar + kWarps;
+  uint64_t* s_empty = s_full + 2;
+  MelPlan* s_plan = reinterpret_cast<MelPlan*>(s_empty + 2);
+  float4* s_frags = reinterpret_cast<float4*>(s_plan + 1);                     // [<= kFragSmemSteps][32]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 32 * 32; i += blockDim.x) s_tw[i] = p.tw2d[i];
+  {
+    const int* src = reinterpret_cast<const int*>(p.plan);
+    int* dst = reinterpret_cast<int*>(s_plan);
+    for (int i = tid; i < (int)(sizeof(MelPlan) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+  }
+  const int total_steps = p.plan->total_steps;
+  const bool frags_in_smem = total_steps <= kFragSmemSteps;
+  if (frags_in_smem)
+    for (int i = tid; i < total_steps * 32; i += blockDim.x) s_frags[i] = p.frags[i];
+  // columns >= 513 of every power row are read by the last k-step: keep them finite (zero)
+  for (int i = tid; i < 2 * kSlots * (kPowPitch - kBins); i += blockDim.x) {
+    const int r = i / (kPowPitch - kBins), c = i - r * (kPowPitch - kBins);
+    s_pow[r * kPowPitch + kBins + c] = 0.f;
+  }
+  if (tid < kWarps) mbar_init(s_bar + tid, 1);
+  if (tid == 0) {
+    mbar_init(s_full + 0, kWarps);
+    mbar_init(s_full + 1, kWarps);
+    mbar_init(s_empty + 0, kMelWarps);
+    mbar_init(s_empty + 1, kMelWarps);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const int64_t stride = (int64_t)gridDim.x * kWarps;
+  const int64_t u0 = (int64_t)blockIdx.x * kWarps;
+  const int width = p.n_mels;
+
+  if (warp < kWarps) {
+    // =============================== transform warps ===========================================
+    reg_alloc<kFftRegs>();
+    float2* tile = s_tile_all + warp * kTileFloat2;
+    float* stage = reinterpret_cast<float*>(tile);
+    uint64_t* bar = s_bar + warp;
+    float wreg[32];
+    load_window(p, lane, wreg);
+    const int half = p.center ? kN / 2 : 0;
+    uint32_t parity = 0;
+    bool staged = false;
+    PairCursor cur;
+    cur.init(u0 + warp, stride, p.pairs_per_row);
+    if (bulk_eligible(p, half, cur.u, cur.pr)) {
+      if (lane == 0) issue_bulk(p, half, cur.row, cur.pr, stage, bar);
+      staged = true;
+    }
+    int it = 0;
+    for (int64_t base = u0; base < p.total_pairs; base += stride, ++it, cur.advance()) {
+      const bool valid = cur.u < p.total_pairs;
+      float pa[17], pb[17];
+      if (valid)
+        transform_pair<POWER_MODE, HG, true>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa, pb);
+      const int b = it & 1;
+      if (it >= 2) mbar_wait(s_empty + b, ((it >> 1) & 1) ^ 1);  // the mel warps have drained this buffer
+      float* prow_a = s_pow + (size_t)(b * kSlots + 2 * warp) * kPowPitch;
       float* prow_b = prow_a + kPowPitch;
       if (valid) {
 #pragma unroll
@@ -473,81 +573,81 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stft1024_kernel(const Pow2Para
         }
       }
       if (lane == 0) {
-        const int64_t oa = valid ? (row * p.frames + ta) * (int64_t)width : -1;
-        s_slot[sb_ + 2 * warp] = oa;
-        s_slot[sb_ + 2 * warp + 1] = (valid && has_b) ? oa + width : -1;
-        const int64_t g = row / p.rows_per_group;
-        s_grp[sb_ + 2 * warp] = g;
-        s_grp[sb_ + 2 * warp + 1] = g;
+        const int64_t ta = 2 * cur.pr;
+        const int64_t oa = valid ? (cur.row * p.frames + ta) * (int64_t)width : -1;
+        s_slot[b * kSlots + 2 * warp] = oa;
+        s_slot[b * kSlots + 2 * warp + 1] = (valid && ta + 1 < p.frames) ? oa + width : -1;
+        const int64_t g = cur.row / p.rows_per_group;
+        s_grp[b * kSlots + 2 * warp] = g;
+        s_grp[b * kSlots + 2 * warp + 1] = g;
       }
-      __syncthreads();  // (1) all 16 power rows are in place
-
-      {  // this warp's items: partial D[16 x 8] = P[16 x chunk] * F[chunk x 8] on the tensor pipe
-        const int r = lane >> 2, c = lane & 3;
-        const int cnt = s_plan->warp_cnt[warp];
-        for (int ii = 0; ii < cnt; ++ii) {
-          const int item = s_plan->warp_items[warp][ii];
-          const MelItem mi = s_plan->items[item];
-          const float* a_lo_row = s_pow + (size_t)r * kPowPitch + mi.kstart + c;
-          const float* a_hi_row = a_lo_row + 8 * kPowPitch;
-          const float4* fr = frag_base + (size_t)mi.frag_off * 32 + lane;
-          // three independent accumulator chains (hi*hi, lo*hi, hi*lo), summed in a fixed order
-          float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-          for (int s = 0; s < mi.nsteps; ++s) {
-            const float4 b = fr[(size_t)s * 32];
-            float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              hi[q] = __float_as_uint(av[q]) & 0xffffe000u;
-              lo[q] = __float_as_uint(av[q] - __uint_as_float(hi[q]));
-            }
-            mma_tf32(d0, hi, __float_as_uint(b.x), __float_as_uint(b.y));
-            mma_tf32(d1, lo, __float_as_uint(b.x), __float_as_uint(b.y));
-            mma_tf32(d2, hi, __float_as_uint(b.z), __float_as_uint(b.w));
-          }
-          float d[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) d[q] = d0[q] + (d1[q] + d2[q]);
-          float2* dst = reinterpret_cast<float2*>(s_part + item * 128 + r * 8 + 2 * c);
-          dst[0] = make_float2(d[0], d[1]);
-          dst[32] = make_float2(d[2], d[3]);  // row r + 8
-        }
-      }
-      __syncthreads();  // (2) all partial products are in place
-
-      {  // fixed-order sum of (up to 4) k-chunks, (dB / log), coalesced store: lane -> filter, warp pairs -> slots
-        for (int nb = 0; nb < p.n_mels; nb += 128) {
-          const int n = nb + (tid & 127);
-          const bool n_ok = n < p.n_mels;
-          const MelTile mt = s_plan->tiles[n_ok ? (n >> 3) : 0];
-          const float* p0 = s_part + mt.part[0] * 128 + (n & 7);
-          const float* p1 = s_part + mt.part[1] * 128 + (n & 7);
-          const float* p2 = s_part + mt.part[2] * 128 + (n & 7);
-          const float* p3 = s_part + mt.part[3] * 128 + (n & 7);
-#pragma unroll
-          for (int si = 0; si < kSlots / 2; ++si) {
-            const int slot = 2 * si + (tid >> 7);
-            float v = (p0[slot * 8] + p1[slot * 8]) + (p2[slot * 8] + p3[slot * 8]);
-            const int64_t dst = s_slot[sb_ + slot];
-            const bool live = n_ok && dst >= 0;
-            if (p.stage == B200A_STAGE_FEAT) {
-              v = p.log_mels ? logf(v + 1e-6f) : p.db_mult * log10f(fmaxf(v, p.db_amin)) - p.db_offset;
-              gmax.add(s_grp[sb_ + slot], v, live);
-            }
-            if (live) p.out[dst + n] = v;
-          }
-        }
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_full + b);
     }
-    cur_row = nxt_row;
-    cur_pr = nxt_pr;
-    nxt_row += step_rows;
-    nxt_pr += step_pairs;
-    if (nxt_pr >= p.pairs_per_row) { nxt_pr -= p.pairs_per_row; ++nxt_row; }
+  } else {
+    // =============================== contraction warps =========================================
+    reg_dealloc<kMelRegs>();
+    const int mw = warp - kWarps;
+    const float4* __restrict__ frag_base = frags_in_smem ? s_frags : p.frags;
+    GroupMax gmax{p.stage == B200A_STAGE_FEAT ? p.group_max : nullptr, -1, -CUDART_INF_F};
+    const int r = lane >> 2, c = lane & 3;
+    const int cnt = s_plan->warp_cnt[mw];
+    int it = 0;
+    for (int64_t base = u0; base < p.total_pairs; base += stride, ++it) {
+      const int b = it & 1;
+      mbar_wait(s_full + b, (it >> 1) & 1);
+      const float* pw = s_pow + (size_t)b * kSlots * kPowPitch;
+      const int64_t o_lo = s_slot[b * kSlots + r], o_hi = s_slot[b * kSlots + r + 8];
+      const int64_t g_lo = s_grp[b * kSlots + r], g_hi = s_grp[b * kSlots + r + 8];
+      for (int ii = 0; ii < cnt; ++ii) {
+        const MelItem mi = s_plan->items[s_plan->warp_items[mw][ii]];
+        const float* a_lo_row = pw + (size_t)r * kPowPitch + mi.kstart + c;
+        const float* a_hi_row = a_lo_row + 8 * kPowPitch;
+        const float4* fr = frag_base + (size_t)mi.frag_off * 32 + lane;
+        // three independent accumulator chains (hi*hi, lo*hi, hi*lo), summed in a fixed order
+        float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int s = 0; s < mi.nsteps; ++s) {
+          const float4 bf = fr[(size_t)s * 32];
+          float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            hi[q] = __float_as_uint(av[q]) & 0xffffe000u;
+            lo[q] = __float_as_uint(av[q] - __uint_as_float(hi[q]));
+          }
+          mma_tf32(d0, hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
+          mma_tf32(d1, lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
+          mma_tf32(d2, hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
+        }
+        float d[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[q] = d0[q] + (d1[q] + d2[q]);
+        const int n0 = 8 * mi.tile + 2 * c;
+        const bool n0_ok = n0 < p.n_mels, n1_ok = n0 + 1 < p.n_mels;
+        if (p.stage == B200A_STAGE_FEAT) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            d[q] = p.log_mels ? logf(d[q] + 1e-6f) : p.db_mult * log10f(fmaxf(d[q], p.db_amin)) - p.db_offset;
+          const float m_lo = fmaxf(n0_ok ? d[0] : -CUDART_INF_F, n1_ok ? d[1] : -CUDART_INF_F);
+          const float m_hi = fmaxf(n0_ok ? d[2] : -CUDART_INF_F, n1_ok ? d[3] : -CUDART_INF_F);
+          gmax.add(g_lo, m_lo, o_lo >= 0);
+          gmax.add(g_hi, m_hi, o_hi >= 0);
+        }
+        if (o_lo >= 0) {
+          if (n1_ok) *reinterpret_cast<float2*>(p.out + o_lo + n0) = make_float2(d[0], d[1]);
+          else if (n0_ok) p.out[o_lo + n0] = d[0];
+        }
+        if (o_hi >= 0) {
+          if (n1_ok) *reinterpret_cast<float2*>(p.out + o_hi + n0) = make_float2(d[2], d[3]);
+          else if (n0_ok) p.out[o_hi + n0] = d[2];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty + b);
+    }
+    gmax.flush();
   }
-  gmax.flush();
 }
 
 // ---- table preparation ------------------------------------------------------------------------
@@ -579,21 +679,10 @@ __global__ void prepare_mma_kernel(const float* __restrict__ fb, const int2* __r
       t_steps[t] = hi > lo ? (hi - t_kstart[t] + 7) / 8 : 0;
       total += t_steps[t];
     }
-    // chunk length: aim at ~2-3 items per warp, never more than kMaxItems in total
-    int chunk = max(4, (total + 2 * kWarps - 1) / (2 * kWarps));
-    for (;;) {  // at most 4 chunks per group and kMaxItems chunks in total
-      int n = 0, worst = 0;
-      for (int t = 0; t < n_tiles; ++t) {
-        const int parts = (t_steps[t] + chunk - 1) / chunk;
-        n += parts;
-        worst = max(worst, parts);
-      }
-      if (n <= kMaxItems && worst <= 4) break;
-      ++chunk;
-    }
+    const int chunk = 1 << 30;  // items are whole filter groups: the contraction warps own complete outputs
     int n_items = 0, off = 0;
     for (int t = 0; t < n_tiles; ++t) {
-      const int parts = (t_steps[t] + chunk - 1) / chunk;
+      const int parts = 1;
       for (int q = 0; q < 4; ++q) plan->tiles[t].part[q] = q < parts ? n_items + q : kMaxItems;
       for (int q = 0; q < parts; ++q) {  // near-equal parts
         const int b0 = (int)((long long)t_steps[t] * q / parts), b1 = (int)((long long)t_steps[t] * (q + 1) / parts);
@@ -605,10 +694,11 @@ __global__ void prepare_mma_kernel(const float* __restrict__ fb, const int2* __r
     plan->n_items = n_items;
     plan->total_steps = total;
     plan->chunk = chunk;
-    // longest-processing-time-first assignment of items to warps
+    // longest-processing-time-first assignment of items to the contraction warps
     int load[kWarps];
     bool used[kMaxItems];
     for (int w = 0; w < kWarps; ++w) { load[w] = 0; plan->warp_cnt[w] = 0; }
+    constexpr int kTargets = 4;  // == kMelWarps
     for (int i = 0; i < n_items; ++i) used[i] = false;
     for (int k = 0; k < n_items; ++k) {
       int best = -1;
@@ -616,13 +706,13 @@ __global__ void prepare_mma_kernel(const float* __restrict__ fb, const int2* __r
         if (!used[i] && (best < 0 || plan->items[i].nsteps > plan->items[best].nsteps)) best = i;
       used[best] = true;
       int w = 0;
-      for (int q = 1; q < kWarps; ++q)
+      for (int q = 1; q < kTargets; ++q)
         if (load[q] < load[w] || (load[q] == load[w] && plan->warp_cnt[q] < plan->warp_cnt[w])) w = q;
       if (plan->warp_cnt[w] >= kMaxItemsPerWarp) {  // cannot happen with kMaxItems <= 2 * kMaxItemsPerWarp
         for (w = 0; plan->warp_cnt[w] >= kMaxItemsPerWarp; ++w) {}
       }
       plan->warp_items[w][plan->warp_cnt[w]++] = best;
-      load[w] += plan->items[best].nsteps;
+      load[w] += plan->items[best].nsteps + 2;  // + epilogue cost
     }
   }
   __syncthreads();
@@ -666,37 +756,60 @@ int pow2_prepare(const b200a_frontend_desc* d, void* ws, size_t ws_bytes, cudaSt
   return launch_status();
 }
 
-template <int POWER_MODE, bool MEL, int HG>
-static int launch_1024(const Pow2Params& p, cudaStream_t stream) {
-  size_t smem = sizeof(float2) * (32 * 32 + kWarps * kTileFloat2) + sizeof(float) * kWarps * kStageFloats +
-                sizeof(int64_t) * 4 * kSlots + sizeof(uint64_t) * kWarps;
-  if (MEL)
-    smem += sizeof(float) * (kSlots * kPowPitch + (kMaxItems + 1) * 128) + sizeof(MelPlan) +
-            sizeof(float4) * 32 * kFragSmemSteps;
-  static_assert(sizeof(MelPlan) % 16 == 0, "fragment array must stay 16-byte aligned");
-  if (smem > 227 * 1024) return B200A_EUNSUPPORTED;
-  auto kern = stft1024_kernel<POWER_MODE, MEL, HG>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-    return B200A_ECUDA;
-  // persistent: one resident CTA per SM, pairs dealt round-robin (every CTA gets the same count +-1)
-  static int num_sms = 0;
-  if (num_sms == 0) {
+static int num_sms() {
+  static int cached = 0;
+  if (cached == 0) {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      return B200A_ECUDA;
-    num_sms = n > 0 ? n : 148;
+      return -1;
+    cached = n > 0 ? n : 148;
   }
+  return cached;
+}
+
+// persistent: one resident CTA per SM, pairs dealt round-robin (every CTA gets the same count +-1)
+static int64_t persistent_grid(const Pow2Params& p) {
+  const int sms = num_sms();
+  if (sms < 0) return -1;
   const int64_t iters = (p.total_pairs + kWarps - 1) / kWarps;
-  int64_t grid = iters < num_sms ? iters : num_sms;
-  if (grid < 1) grid = 1;
+  const int64_t grid = iters < sms ? iters : sms;
+  return grid < 1 ? 1 : grid;
+}
+
+template <int POWER_MODE, int HG>
+static int launch_power(const Pow2Params& p, cudaStream_t stream) {
+  const size_t smem = sizeof(float2) * (32 * 32 + kWarps * kTileFloat2) + sizeof(float) * kWarps * kStageFloats +
+                      sizeof(uint64_t) * kWarps;
+  auto kern = stft1024_power_kernel<POWER_MODE, HG>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return B200A_ECUDA;
+  const int64_t grid = persistent_grid(p);
+  if (grid < 0) return B200A_ECUDA;
   kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(p);
   return launch_status();
 }
 
-template <int POWER_MODE, bool MEL>
-static int launch_hg(const Pow2Params& p, cudaStream_t stream) {
-  if (p.bulk_ok && p.hop == 256) return launch_1024<POWER_MODE, MEL, 8>(p, stream);
-  return launch_1024<POWER_MODE, MEL, -1>(p, stream);
+template <int POWER_MODE, int HG>
+static int launch_mel(const Pow2Params& p, cudaStream_t stream) {
+  static_assert(sizeof(MelPlan) % 16 == 0, "fragment array must stay 16-byte aligned");
+  const size_t smem = sizeof(float2) * (32 * 32 + kWarps * kTileFloat2) + sizeof(float) * 2 * kSlots * kPowPitch +
+                      sizeof(int64_t) * 4 * kSlots + sizeof(uint64_t) * (kWarps + 4) + sizeof(MelPlan) +
+                      sizeof(float4) * 32 * kFragSmemSteps;
+  if (smem > 227 * 1024) return B200A_EUNSUPPORTED;
+  auto kern = stft1024_mel_kernel<POWER_MODE, HG>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return B200A_ECUDA;
+  const int64_t grid = persistent_grid(p);
+  if (grid < 0) return B200A_ECUDA;
+  kern<<<(unsigned)grid, (kWarps + kMelWarps) * 32, smem, stream>>>(p);
+  return launch_status();
+}
+
+template <int POWER_MODE>
+static int launch_hg(const Pow2Params& p, bool mel, cudaStream_t stream) {
+  const bool aligned_b = p.bulk_ok && p.hop == 256;
+  if (mel) return aligned_b ? launch_mel<POWER_MODE, 8>(p, stream) : launch_mel<POWER_MODE, -1>(p, stream);
+  return aligned_b ? launch_power<POWER_MODE, 8>(p, stream) : launch_power<POWER_MODE, -1>(p, stream);
 }
 
 int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, const float* wave, int64_t rows,
@@ -738,8 +851,7 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
   p.bulk_ok = d->hop <= kMaxHopBulk && d->hop % 4 == 0 && (half + d->pad) % 4 == 0 && row_stride % 4 == 0 &&
               (reinterpret_cast<uintptr_t>(wave) & 15) == 0;
   const bool mel = stage >= B200A_STAGE_MEL;
-  if (d->power == 2.f) return mel ? launch_hg<2, true>(p, stream) : launch_hg<2, false>(p, stream);
-  return mel ? launch_hg<0, true>(p, stream) : launch_hg<0, false>(p, stream);
+  return d->power == 2.f ? launch_hg<2>(p, mel, stream) : launch_hg<0>(p, mel, stream);
 }
 
 }  // namespace b200a
