@@ -29,6 +29,7 @@
 #include <utility>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace b200a {
 
@@ -161,45 +162,6 @@ __device__ __forceinline__ void fft32(float2 (&a)[32]) {
   });
 }
 
-// ---- mbarrier / bulk-copy / mma PTX -----------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// Bounded wait: a mis-programmed copy traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  for (int spin = 0; spin < (1 << 24); ++spin) {
-    uint32_t ok;
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-  }
-  __trap();
-}
-
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
 struct Pow2Params {
   const float* wave;
   int64_t length, row_stride, frames, pairs_per_row, total_pairs;
@@ -254,10 +216,6 @@ struct GroupMax {
   }
 };
 
-// ---- mbarrier arrive (release, CTA scope) --------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 template <int N>
 __device__ __forceinline__ void reg_alloc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
@@ -488,7 +446,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stft1024_power_kernel(const Po
 // the tile's full/empty mbarriers, so the FFT warps never wait for the contraction.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMelWarps = 4;
-constexpr int kFftRegs = 216, kMelRegs = 64;  // 256*216 + 128*64 = 63488 <= 64512 = 384 * 168
+constexpr int kFftRegs = 200, kMelRegs = 96;  // 256*200 + 128*96 = 63488 <= 64512 = 384 * 168
 
 template <int POWER_MODE, int HG>
 __global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft1024_mel_kernel(const Pow2Params p) {
@@ -606,7 +564,7 @@ __global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft1024_mel_ker
         const float4* fr = frag_base + (size_t)mi.frag_off * 32 + lane;
         // three independent accumulator chains (hi*hi, lo*hi, hi*lo), summed in a fixed order
         float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
+#pragma unroll 4
         for (int s = 0; s < mi.nsteps; ++s) {
           const float4 bf = fr[(size_t)s * 32];
           float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};

@@ -4,32 +4,64 @@
 // conv1d with a (new', 1, 2*width+orig') filter and stride orig'
 // (src/torchaudio/functional/functional.py:1405-1432).  Almost all of every filter row is
 // (numerically) zero: row j only has a contiguous run of ~2*lowpass_width*orig'/min(orig',new')
-// taps around the position of output phase j.  `resample_prepare` finds that run per phase once,
-// the kernels then touch only those taps -- no padded copy of the input, no (rows, new', frames)
-// intermediate, output written already interleaved and truncated.
+// taps around the position of output phase j.
+//
+// Main kernel (resample_mma_kernel): the sum IS a banded matrix product
+//     Y[f][j] = sum_i X[f][i] * K[j][i],   X[f][i] = x[f*orig' + i - width]  (a strided view of the signal)
+// so a CTA stages the samples of 32 output frames in shared memory with one bulk asynchronous copy
+// (double buffered: the next tile lands while this one is multiplied), and its 8 warps run
+// mma.sync.m16n8k8 TF32 tiles of 16 frames x 8 phases over just the k-steps where those 8 phases have
+// live taps, with error-compensated operands (X_hi*K_hi + X_lo*K_hi + X_hi*K_lo, ~2^-21 relative).
+// No padded copy of the input, no (rows, new', frames) intermediate; the output is written already
+// interleaved and truncated.  Each input sample is read from HBM once, each output written once.
+//
+// Fallback (resample_direct_kernel): one output per thread over the phase's live taps, for ratios whose
+// tables or tiles do not fit (new' > 1024, orig' > ~1100) or mis-aligned inputs.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace b200a {
 
+namespace {
+
+constexpr int kRsWarps = 8;
+constexpr int kRsFrames = 32;        // frames per CTA tile (two 16-row MMA tiles)
+constexpr int kRsMaxTiles = 128;     // groups of 8 phases  (new' <= 1024)
+constexpr int kRsFragSmemBytes = 72 * 1024;
+constexpr int kRsSmemBudget = 224 * 1024;
+
+struct RsTile {  // one group of 8 phases
+  int kstart;    // first tap of its first k-step (multiple of 8)
+  int nsteps;    // 8-tap k-steps covering the union of the group's live taps
+  int frag_off;  // first step in the fragment array
+  int pad;
+};
+
 struct RsHeader {
   uint32_t magic;
-  int32_t orig_r, new_r, width, taps, max_support;
-  int32_t reserved[10];
+  int32_t orig_r, new_r, width, taps, max_support, n_tiles, total_steps;
+  int32_t reserved[8];
 };
 static_assert(sizeof(RsHeader) == 64, "header is 64 bytes");
 
 struct RsLayout {
-  size_t header, support, total;
+  size_t header, support, tiles, frags, total;
 };
 
+inline int rs_tiles(int new_r) { return (new_r + 7) / 8; }
+
 inline RsLayout rs_layout(int new_r, int taps) {
-  (void)taps;
   RsLayout l{};
   size_t off = 0;
   l.header = off;
   off = align_up(off + sizeof(RsHeader), 256);
   l.support = off;
   off = align_up(off + sizeof(int2) * (size_t)new_r, 256);
+  l.tiles = off;
+  off = align_up(off + sizeof(RsTile) * (size_t)rs_tiles(new_r), 256);
+  l.frags = off;  // worst case: every group spans every tap
+  const size_t nt = rs_tiles(new_r) <= kRsMaxTiles ? rs_tiles(new_r) : 0;
+  off = align_up(off + sizeof(float4) * 32 * nt * ((size_t)taps / 8 + 2), 256);
   l.total = off;
   return l;
 }
@@ -70,6 +102,180 @@ __global__ void resample_support_kernel(const float* __restrict__ kernel, int ne
   }
 }
 
+// Per group of 8 phases: the k-steps its live taps span, and the taps split into TF32 hi/lo parts in
+// mma.m16n8k8 B-fragment order (B[k][n] = K[8 t + n][kstart + k]).
+__global__ void resample_plan_kernel(const float* __restrict__ kernel, const int2* __restrict__ support, int new_r,
+                                     int taps, int n_tiles, RsHeader* hdr, RsTile* tiles, float4* frags) {
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      int lo = taps, hi = 0;
+      for (int j = 8 * t; j < min(8 * t + 8, new_r); ++j) {
+        const int2 sp = support[j];
+        if (sp.y > 0) { lo = min(lo, sp.x); hi = max(hi, sp.x + sp.y); }
+      }
+      RsTile rt{0, 0, acc, 0};
+      if (hi > lo) {
+        rt.kstart = lo & ~7;
+        rt.nsteps = (hi - rt.kstart + 7) / 8;
+      }
+      tiles[t] = rt;
+      acc += rt.nsteps;
+    }
+    hdr->n_tiles = n_tiles;
+    hdr->total_steps = acc;
+  }
+  __syncthreads();
+  for (int t = 0; t < n_tiles; ++t) {
+    const RsTile rt = tiles[t];
+    for (int i = threadIdx.x; i < rt.nsteps * 32; i += blockDim.x) {
+      const int s = i >> 5, lane = i & 31;
+      const int j = 8 * t + (lane >> 2);
+      const int k0 = rt.kstart + 8 * s + (lane & 3), k1 = k0 + 4;
+      const float b0 = (j < new_r && k0 < taps) ? kernel[(size_t)j * taps + k0] : 0.f;
+      const float b1 = (j < new_r && k1 < taps) ? kernel[(size_t)j * taps + k1] : 0.f;
+      const float b0h = __uint_as_float(__float_as_uint(b0) & 0xffffe000u);
+      const float b1h = __uint_as_float(__float_as_uint(b1) & 0xffffe000u);
+      frags[(size_t)(rt.frag_off + s) * 32 + lane] = make_float4(b0h, b1h, b0 - b0h, b1 - b1h);
+    }
+  }
+}
+
+struct RsParams {
+  const float* wave;
+  int64_t rows, length, row_stride;
+  float* out;
+  int64_t out_row_stride, out_len;
+  const RsHeader* hdr;
+  const RsTile* tiles;
+  const float4* frags;
+  int orig_r, new_r, width, taps, n_tiles;
+  int64_t frames;           // output frames per row = ceil(out_len / new_r)
+  int64_t blocks_per_row;   // ceil(frames / kRsFrames)
+  int64_t total_blocks;
+  int xs_floats;            // floats per staging buffer
+  int frag_smem_bytes;      // shared memory granted to the fragment copy (0: read them from global)
+};
+
+// Fill one staging buffer with the samples frames [f0, f0 + 32) of `row` need:
+// xs[q] = x[T0 + q - shift] (zero outside the signal), T0 = f0*orig' - width, shift = (-T0) mod 4 so that
+// 16-byte aligned global addresses land on 16-byte aligned shared addresses for the bulk copy.
+__device__ __forceinline__ int rs_fill(const RsParams& p, int64_t row, int64_t f0, float* xs, uint64_t* bar, int tid,
+                                       int nthreads) {
+  const int64_t T0 = f0 * p.orig_r - p.width;
+  const float* x = p.wave + row * p.row_stride;
+  // word address of sample g is a0 + g (mod 4): the bulk copy needs 16-byte aligned global AND shared
+  // addresses, so the tile is shifted by 0..3 floats until the two alignments agree
+  const int a0 = (int)((reinterpret_cast<uintptr_t>(x) >> 2) & 3);
+  const int shift = (int)((((a0 + T0) % 4) + 4) % 4);  // xs index of sample g: q = g - T0 + shift == a0 + g (mod 4)
+  const int64_t span = (int64_t)kRsFrames * p.orig_r + p.taps + 8;
+  const int64_t lo = T0 < 0 ? 0 : T0;
+  int64_t hi = T0 + span;
+  if (hi > p.length) hi = p.length;
+  if (hi < lo) hi = lo;
+  const int64_t lo_a = lo + ((4 - ((a0 + lo) & 3)) & 3);  // first sample >= lo on a 16-byte boundary
+  const int64_t hi_a = hi - ((a0 + hi) & 3);               // last 16-byte boundary <= hi; bulk part [lo_a, hi_a)
+  const int q_lo = (int)(lo - T0) + shift, q_hi = (int)(hi - T0) + shift;
+  // zeros before the signal / after it, scalar loads for the unaligned head and tail
+  for (int q = tid; q < p.xs_floats; q += nthreads) {
+    const int64_t g = T0 + q - shift;
+    if (q < q_lo || q >= q_hi) xs[q] = 0.f;
+    else if (g < lo_a || g >= hi_a || hi_a <= lo_a) xs[q] = x[g];
+  }
+  if (tid == 0) {
+    if (hi_a > lo_a) {
+      const uint32_t bytes = (uint32_t)(hi_a - lo_a) * 4u;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(xs + (lo_a - T0) + shift, x + lo_a, bytes, bar);
+    } else {
+      mbar_arrive(bar);  // nothing to copy: complete the phase
+    }
+  }
+  return shift;
+}
+
+__global__ void __launch_bounds__(kRsWarps * 32, 1) resample_mma_kernel(const RsParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_x = reinterpret_cast<float*>(smem_raw);                              // [2][xs_floats]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_x + 2 * (size_t)p.xs_floats);  // [2]
+  RsTile* s_tiles = reinterpret_cast<RsTile*>(s_bar + 2);                       // [n_tiles]
+  float4* s_frags = reinterpret_cast<float4*>(s_tiles + ((p.n_tiles + 3) & ~3));  // optional
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < p.n_tiles; i += blockDim.x) s_tiles[i] = p.tiles[i];
+  const int total_steps = p.hdr->total_steps;
+  const bool frags_in_smem = (size_t)total_steps * 512 <= (size_t)p.frag_smem_bytes;
+  if (frags_in_smem)
+    for (int i = tid; i < total_steps * 32; i += blockDim.x) s_frags[i] = p.frags[i];
+  const float4* __restrict__ frag_base = frags_in_smem ? s_frags : p.frags;
+  if (tid == 0) {
+    mbar_init(s_bar + 0, 1);
+    mbar_init(s_bar + 1, 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  int shift[2] = {0, 0};
+  int64_t blk = blockIdx.x;
+  if (blk < p.total_blocks) {
+    const int64_t row = blk / p.blocks_per_row, fb = blk - row * p.blocks_per_row;
+    shift[0] = rs_fill(p, row, fb * kRsFrames, s_x, s_bar + 0, tid, blockDim.x);
+  }
+  const int r = lane >> 2, c = lane & 3;
+  const int n_items = 2 * p.n_tiles;  // (16-frame half, phase group)
+  for (int it = 0; blk < p.total_blocks; blk += gridDim.x, ++it) {
+    const int b = it & 1;
+    const int64_t nxt = blk + gridDim.x;
+    if (nxt < p.total_blocks) {  // stage the next tile into the other buffer (its readers finished last iteration)
+      const int64_t nrow = nxt / p.blocks_per_row, nfb = nxt - nrow * p.blocks_per_row;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      shift[b ^ 1] = rs_fill(p, nrow, nfb * kRsFrames, s_x + (size_t)(b ^ 1) * p.xs_floats, s_bar + (b ^ 1), tid,
+                             blockDim.x);
+    }
+    mbar_wait(s_bar + b, (it >> 1) & 1);
+    __syncthreads();  // the scalar part of the fill is visible too
+
+    const int64_t row = blk / p.blocks_per_row, fb = blk - row * p.blocks_per_row;
+    const int64_t f0 = fb * kRsFrames;
+    const float* xs = s_x + (size_t)b * p.xs_floats + shift[b];
+    float* orow = p.out + row * p.out_row_stride;
+    for (int item = warp; item < n_items; item += kRsWarps) {
+      const int half = item & 1, t = item >> 1;
+      const RsTile rt = s_tiles[t];
+      // A[f][i] = xs[f*orig' + i]: rows r and r + 8 of this 16-frame half
+      const float* a_lo_row = xs + (size_t)(16 * half + r) * p.orig_r + rt.kstart + c;
+      const float* a_hi_row = a_lo_row + (size_t)8 * p.orig_r;
+      const float4* fr = frag_base + (size_t)rt.frag_off * 32 + lane;
+      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+      for (int s = 0; s < rt.nsteps; ++s) {
+        const float4 bf = fr[(size_t)s * 32];
+        const float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split_tf32(av[q], hi[q], lo[q]);
+        mma_tf32(d0, hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
+        mma_tf32(d1, lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
+        mma_tf32(d2, hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
+      }
+      // D rows r, r+8 = frames; columns 2c, 2c+1 = phases 8t + 2c (+1): out index = f*new' + phase
+      const int j0 = 8 * t + 2 * c;
+      const int64_t m_lo = (f0 + 16 * half + r) * p.new_r + j0, m_hi = m_lo + (int64_t)8 * p.new_r;
+      const float v0 = d0[0] + (d1[0] + d2[0]), v1 = d0[1] + (d1[1] + d2[1]);
+      const float v2 = d0[2] + (d1[2] + d2[2]), v3 = d0[3] + (d1[3] + d2[3]);
+      if (j0 < p.new_r) {
+        if (m_lo < p.out_len) orow[m_lo] = v0;
+        if (m_hi < p.out_len) orow[m_hi] = v2;
+      }
+      if (j0 + 1 < p.new_r) {
+        if (m_lo + 1 < p.out_len) orow[m_lo + 1] = v1;
+        if (m_hi + 1 < p.out_len) orow[m_hi + 1] = v3;
+      }
+    }
+    __syncthreads();  // everyone is done with buffer b before it is refilled
+  }
+}
+
 // Straightforward one-output-per-thread kernel (any ratio).  Consecutive threads are consecutive
 // output samples, i.e. consecutive phases of the same input neighbourhood: input loads hit L1.
 __global__ void __launch_bounds__(256)
@@ -95,6 +301,8 @@ resample_direct_kernel(const float* __restrict__ wave, int64_t length, int64_t r
   }
 }
 
+}  // namespace
+
 size_t resample_workspace_bytes_impl(int new_r, int taps) { return rs_layout(new_r, taps).total; }
 
 int resample_prepare_impl(const float* kernel, int orig_r, int new_r, int width, void* ws, size_t ws_bytes,
@@ -105,9 +313,13 @@ int resample_prepare_impl(const float* kernel, int orig_r, int new_r, int width,
   if (ws_bytes < l.total) return B200A_EWORKSPACE;
   unsigned char* base = static_cast<unsigned char*>(ws);
   if (cudaMemsetAsync(base + l.header, 0, sizeof(RsHeader), stream) != cudaSuccess) return B200A_ECUDA;
-  resample_support_kernel<<<(new_r + 7) / 8, 256, 0, stream>>>(kernel, new_r, taps, orig_r, width,
-                                                               reinterpret_cast<RsHeader*>(base + l.header),
-                                                               reinterpret_cast<int2*>(base + l.support));
+  RsHeader* hdr = reinterpret_cast<RsHeader*>(base + l.header);
+  int2* support = reinterpret_cast<int2*>(base + l.support);
+  resample_support_kernel<<<(new_r + 7) / 8, 256, 0, stream>>>(kernel, new_r, taps, orig_r, width, hdr, support);
+  if (rs_tiles(new_r) <= kRsMaxTiles)
+    resample_plan_kernel<<<1, 256, 0, stream>>>(kernel, support, new_r, taps, rs_tiles(new_r), hdr,
+                                                reinterpret_cast<RsTile*>(base + l.tiles),
+                                                reinterpret_cast<float4*>(base + l.frags));
   return launch_status();
 }
 
@@ -117,10 +329,55 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
   if (orig_r < 1 || new_r < 1 || width < 0 || rows < 0 || length < 0 || out_len < 0) return B200A_EINVAL;
   if (rows == 0 || out_len == 0) return B200A_OK;  // empty batch: pointers may be null
   if (ws == nullptr || kernel == nullptr || wave == nullptr || out == nullptr) return B200A_EINVAL;
-  if (rows > 65535) return B200A_EUNSUPPORTED;
   const int taps = 2 * width + orig_r;
   const RsLayout l = rs_layout(new_r, taps);
   const unsigned char* base = static_cast<const unsigned char*>(ws);
+
+  // ---- tensor-pipe path -------------------------------------------------------------------------
+  const int n_tiles = rs_tiles(new_r);
+  const int xs_floats = (kRsFrames * orig_r + taps + 8 + 4 + 3) & ~3;
+  const size_t smem_fixed = sizeof(float) * 2 * (size_t)xs_floats + 16 + sizeof(RsTile) * ((n_tiles + 3) & ~3);
+  const bool aligned = (reinterpret_cast<uintptr_t>(wave) & 3) == 0;  // any float pointer; rows may have any pitch
+  if (n_tiles <= kRsMaxTiles && aligned && smem_fixed + 1024 <= (size_t)kRsSmemBudget) {
+    RsParams p{};
+    p.wave = wave;
+    p.rows = rows;
+    p.length = length;
+    p.row_stride = row_stride;
+    p.out = out;
+    p.out_row_stride = out_row_stride;
+    p.out_len = out_len;
+    p.hdr = reinterpret_cast<const RsHeader*>(base + l.header);
+    p.tiles = reinterpret_cast<const RsTile*>(base + l.tiles);
+    p.frags = reinterpret_cast<const float4*>(base + l.frags);
+    p.orig_r = orig_r;
+    p.new_r = new_r;
+    p.width = width;
+    p.taps = taps;
+    p.n_tiles = n_tiles;
+    p.frames = (out_len + new_r - 1) / new_r;
+    p.blocks_per_row = (p.frames + kRsFrames - 1) / kRsFrames;
+    p.total_blocks = rows * p.blocks_per_row;
+    p.xs_floats = xs_floats;
+    // fragments go to shared memory when they fit next to the staging buffers (the kernel compares the
+    // device-side step count with the room granted here), otherwise they are read through L1
+    p.frag_smem_bytes = smem_fixed + kRsFragSmemBytes <= (size_t)kRsSmemBudget ? kRsFragSmemBytes : 0;
+    const size_t smem = smem_fixed + p.frag_smem_bytes;
+    if (cudaFuncSetAttribute(resample_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess)
+      return B200A_ECUDA;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return B200A_ECUDA;
+    int64_t grid = p.total_blocks < sms ? p.total_blocks : sms;
+    if (grid < 1) grid = 1;
+    resample_mma_kernel<<<(unsigned)grid, kRsWarps * 32, smem, stream>>>(p);
+    return launch_status();
+  }
+
+  // ---- direct path --------------------------------------------------------------------------------
+  if (rows > 65535) return B200A_EUNSUPPORTED;
   unsigned bx = (unsigned)((out_len + 255) / 256);
   if (bx > 4096) bx = 4096;
   dim3 grid(bx, (unsigned)rows);
