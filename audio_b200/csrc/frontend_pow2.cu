@@ -26,6 +26,7 @@
 //
 // Reference semantics: src/torchaudio/functional/functional.py:54-145 and
 // transforms/_transforms.py:403-415, :701-705 (see frontend_generic.cu for the any-size path).
+#include <type_traits>
 #include <utility>
 
 #include "common.cuh"
@@ -546,7 +547,6 @@ __global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft1024_mel_ker
     // =============================== contraction warps =========================================
     reg_dealloc<kMelRegs>();
     const int mw = warp - kWarps;
-    const float4* __restrict__ frag_base = frags_in_smem ? s_frags : p.frags;
     GroupMax gmax{p.stage == B200A_STAGE_FEAT ? p.group_max : nullptr, -1, -CUDART_INF_F};
     const int r = lane >> 2, c = lane & 3;
     const int cnt = s_plan->warp_cnt[mw];
@@ -561,23 +561,26 @@ __global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft1024_mel_ker
         const MelItem mi = s_plan->items[s_plan->warp_items[mw][ii]];
         const float* a_lo_row = pw + (size_t)r * kPowPitch + mi.kstart + c;
         const float* a_hi_row = a_lo_row + 8 * kPowPitch;
-        const float4* fr = frag_base + (size_t)mi.frag_off * 32 + lane;
         // three independent accumulator chains (hi*hi, lo*hi, hi*lo), summed in a fixed order
         float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+        auto contract = [&](auto in_smem) {
+          const float4* fr = (decltype(in_smem)::value ? s_frags : p.frags) + (size_t)mi.frag_off * 32 + lane;
 #pragma unroll 4
-        for (int s = 0; s < mi.nsteps; ++s) {
-          const float4 bf = fr[(size_t)s * 32];
-          float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
-          uint32_t hi[4], lo[4];
+          for (int s = 0; s < mi.nsteps; ++s) {
+            float4 bf;
+            if constexpr (decltype(in_smem)::value) bf = fr[(size_t)s * 32];
+            else bf = __ldg(fr + (size_t)s * 32);
+            const float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
+            uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            hi[q] = __float_as_uint(av[q]) & 0xffffe000u;
-            lo[q] = __float_as_uint(av[q] - __uint_as_float(hi[q]));
+            for (int q = 0; q < 4; ++q) split_tf32(av[q], hi[q], lo[q]);
+            mma_tf32(d0, hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
+            mma_tf32(d1, lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
+            mma_tf32(d2, hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
           }
-          mma_tf32(d0, hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
-          mma_tf32(d1, lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
-          mma_tf32(d2, hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
-        }
+        };
+        if (frags_in_smem) contract(std::true_type{});
+        else contract(std::false_type{});
         float d[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) d[q] = d0[q] + (d1[q] + d2[q]);

@@ -17,6 +17,8 @@
 //
 // Fallback (resample_direct_kernel): one output per thread over the phase's live taps, for ratios whose
 // tables or tiles do not fit (new' > 1024, orig' > ~1100) or mis-aligned inputs.
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -27,7 +29,6 @@ namespace {
 constexpr int kRsWarps = 8;
 constexpr int kRsFrames = 32;        // frames per CTA tile (two 16-row MMA tiles)
 constexpr int kRsMaxTiles = 128;     // groups of 8 phases  (new' <= 1024)
-constexpr int kRsFragSmemBytes = 72 * 1024;
 constexpr int kRsSmemBudget = 224 * 1024;
 
 struct RsTile {  // one group of 8 phases
@@ -176,11 +177,18 @@ __device__ __forceinline__ int rs_fill(const RsParams& p, int64_t row, int64_t f
   const int64_t lo_a = lo + ((4 - ((a0 + lo) & 3)) & 3);  // first sample >= lo on a 16-byte boundary
   const int64_t hi_a = hi - ((a0 + hi) & 3);               // last 16-byte boundary <= hi; bulk part [lo_a, hi_a)
   const int q_lo = (int)(lo - T0) + shift, q_hi = (int)(hi - T0) + shift;
-  // zeros before the signal / after it, scalar loads for the unaligned head and tail
-  for (int q = tid; q < p.xs_floats; q += nthreads) {
-    const int64_t g = T0 + q - shift;
-    if (q < q_lo || q >= q_hi) xs[q] = 0.f;
-    else if (g < lo_a || g >= hi_a || hi_a <= lo_a) xs[q] = x[g];
+  // zeros where the tile sticks out of the signal (only edge tiles), scalar loads for the (< 4 sample)
+  // unaligned head and tail of the bulk range
+  if (q_lo > 0 && T0 < 0)
+    for (int q = tid; q < q_lo; q += nthreads) xs[q] = 0.f;
+  if (hi < T0 + span)
+    for (int q = q_hi + tid; q < p.xs_floats; q += nthreads) xs[q] = 0.f;
+  if (hi_a > lo_a) {
+    const int head = (int)(lo_a - lo), tail = (int)(hi - hi_a);
+    if (tid < head) xs[q_lo + tid] = x[lo + tid];
+    else if (tid >= 32 && tid < 32 + tail) xs[(int)(hi_a - T0) + shift + (tid - 32)] = x[hi_a + (tid - 32)];
+  } else {
+    for (int q = q_lo + tid; q < q_hi; q += nthreads) xs[q] = x[T0 + q - shift];
   }
   if (tid == 0) {
     if (hi_a > lo_a) {
@@ -207,7 +215,6 @@ __global__ void __launch_bounds__(kRsWarps * 32, 1) resample_mma_kernel(const Rs
   const bool frags_in_smem = (size_t)total_steps * 512 <= (size_t)p.frag_smem_bytes;
   if (frags_in_smem)
     for (int i = tid; i < total_steps * 32; i += blockDim.x) s_frags[i] = p.frags[i];
-  const float4* __restrict__ frag_base = frags_in_smem ? s_frags : p.frags;
   if (tid == 0) {
     mbar_init(s_bar + 0, 1);
     mbar_init(s_bar + 1, 1);
@@ -245,19 +252,25 @@ __global__ void __launch_bounds__(kRsWarps * 32, 1) resample_mma_kernel(const Rs
       // A[f][i] = xs[f*orig' + i]: rows r and r + 8 of this 16-frame half
       const float* a_lo_row = xs + (size_t)(16 * half + r) * p.orig_r + rt.kstart + c;
       const float* a_hi_row = a_lo_row + (size_t)8 * p.orig_r;
-      const float4* fr = frag_base + (size_t)rt.frag_off * 32 + lane;
       float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+      auto contract = [&](auto in_smem) {
+        const float4* fr = (decltype(in_smem)::value ? s_frags : p.frags) + (size_t)rt.frag_off * 32 + lane;
 #pragma unroll 2
-      for (int s = 0; s < rt.nsteps; ++s) {
-        const float4 bf = fr[(size_t)s * 32];
-        const float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
-        uint32_t hi[4], lo[4];
+        for (int s = 0; s < rt.nsteps; ++s) {
+          float4 bf;
+          if constexpr (decltype(in_smem)::value) bf = fr[(size_t)s * 32];
+          else bf = __ldg(fr + (size_t)s * 32);
+          const float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
+          uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) split_tf32(av[q], hi[q], lo[q]);
-        mma_tf32(d0, hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
-        mma_tf32(d1, lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
-        mma_tf32(d2, hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
-      }
+          for (int q = 0; q < 4; ++q) split_tf32(av[q], hi[q], lo[q]);
+          mma_tf32(d0, hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
+          mma_tf32(d1, lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
+          mma_tf32(d2, hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
+        }
+      };
+      if (frags_in_smem) contract(std::true_type{});
+      else contract(std::false_type{});
       // D rows r, r+8 = frames; columns 2c, 2c+1 = phases 8t + 2c (+1): out index = f*new' + phase
       const int j0 = 8 * t + 2 * c;
       const int64_t m_lo = (f0 + 16 * half + r) * p.new_r + j0, m_hi = m_lo + (int64_t)8 * p.new_r;
@@ -361,7 +374,7 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
     p.xs_floats = xs_floats;
     // fragments go to shared memory when they fit next to the staging buffers (the kernel compares the
     // device-side step count with the room granted here), otherwise they are read through L1
-    p.frag_smem_bytes = smem_fixed + kRsFragSmemBytes <= (size_t)kRsSmemBudget ? kRsFragSmemBytes : 0;
+    p.frag_smem_bytes = (int)(((size_t)kRsSmemBudget - smem_fixed) & ~(size_t)511);  // everything that is left
     const size_t smem = smem_fixed + p.frag_smem_bytes;
     if (cudaFuncSetAttribute(resample_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess)
