@@ -1,28 +1,29 @@
-// Register-FFT fast path of the fused front end (n_fft = 1024, one-sided, real output stages).
+// Register-FFT fast path of the fused front end (n_fft = 256 / 512 / 1024, one-sided, real output stages).
 //
-// One WARP transforms one PAIR of consecutive frames (a, b) of an utterance; a CTA of 8 warps
-// therefore finishes 16 frames per iteration:
-//   input   the 1024+hop contiguous samples of the pair are staged into shared memory by ONE
-//           bulk async copy (cp.async.bulk + mbarrier, the TMA engine's 1-D mode), issued one
-//           iteration ahead so its latency hides behind the previous pair's arithmetic
-//   z[n] = w[n] * (a[n] + i b[n]),  n = lane + 32 j      -- 32 complex values per lane
+// A group of G = n_fft/32 lanes transforms one PAIR of consecutive frames (a, b); a warp holds 32/G
+// such groups (1, 2 or 4 pairs = 2, 4 or 8 consecutive frames of one utterance = one "unit"):
+//   input   the unit's n_fft + (frames-1)*hop contiguous samples are staged into shared memory by ONE
+//           bulk asynchronous copy (cp.async.bulk + mbarrier, the TMA engine's 1-D mode), issued a
+//           unit ahead so its latency hides behind the previous unit's arithmetic
+//   z[n] = w[n] * (a[n] + i b[n]),  n = g + G j          -- 32 complex values per lane
 //   pass 1  32-point DFT over j in registers (radix-2 DIT, compile-time twiddles, FMA-form butterflies)
-//   twiddle W_1024^(lane * k2) from a shared 32x32 table, transpose through a padded per-warp tile
-//   pass 2  32-point DFT over the former lane index in registers  -> Z[lane + 32 k1]
+//   twiddle W_nfft^(g * k2) from a shared 32 x G table, transpose through a padded per-warp shared tile
+//   pass 2  32/G DFTs of G points over the former lane index, in registers  -> Z[l + G q + 32 k1]
 //   un-pack the two real spectra with one shuffle per needed value:  A = (Z[k] + conj Z[N-k]) / 2,
 //                                                                    B = (Z[k] - conj Z[N-k]) / 2i
-//   |.|^p -> global (Spectrogram), or -> a shared [16 frames x 520 bins] power tile.
-//   mel     all 8 warps then contract the power tile with the filterbank on the tensor pipe:
-//           warp-level mma.sync m16n8k8 TF32 with error-compensated operands
-//           (P_hi*F_hi + P_lo*F_hi + P_hi*F_lo, ~2^-21 relative), visiting only the k-steps where a
-//           group of 8 filters is non-zero; (-> dB / log) -> global.
+//   every lane ends with bins k = l + G m (m < 16) of its two frames; |.|^p -> global (Spectrogram), or
+//   -> a double-buffered shared power tile of all frames the CTA finished this iteration.
+//   mel     warp specialised: 8 transform warps publish power rows, 4 contraction warps multiply each
+//           finished tile with the filterbank on the tensor pipe: mma.sync m16n8k8 TF32 with
+//           error-compensated operands (P_hi*F_hi + P_lo*F_hi + P_hi*F_lo, ~2^-21 relative), visiting
+//           only the k-steps where a group of 8 filters is non-zero; (-> dB / log) -> global.
 // Nothing but the waveform is read from HBM and nothing but the final features is written.
 //
 // Why mma.sync and not tcgen05 for the mel contraction: a tcgen05.mma tile needs M >= 64 frames of
 // the A operand resident (64 x 513 power values in two bf16 planes or one fp32 plane = 131 KB, or
 // > 512 TMEM columns) next to the FFT working set of the warps that produce them; that does not fit
-// the 227 KB of shared memory per SM at n_fft = 1024.  The warp-level fragment MMA has M = 16, which is
-// exactly one CTA iteration.  See DESIGN.md ("mel projection").
+// the 227 KB of shared memory per SM at n_fft = 1024.  The warp-level fragment MMA has M = 16.
+// See DESIGN.md ("mel projection").
 //
 // Reference semantics: src/torchaudio/functional/functional.py:54-145 and
 // transforms/_transforms.py:403-415, :701-705 (see frontend_generic.cu for the any-size path).
@@ -36,38 +37,44 @@ namespace b200a {
 
 namespace {
 
-constexpr int kN = 1024;
-constexpr int kBins = kN / 2 + 1;
-constexpr int kWarps = 8;
-constexpr int kSlots = 2 * kWarps;               // frames finished per CTA iteration
-constexpr int kTileLd = 33;                      // float2 row pitch of the transpose tile (bank-conflict free)
-constexpr int kTileFloat2 = 32 * kTileLd;        // per warp
-constexpr int kPowPitch = 548;                   // floats per power row: >= 520 and == 4 (mod 32)
-constexpr int kMaxHopBulk = 256;                 // staging buffer holds 1024 + hop samples
-constexpr int kStageFloats = kN + kMaxHopBulk;
-constexpr int kMaxItems = 64;                    // filter groups (of 8) per contraction
+constexpr int kWarps = 8;     // transform warps per CTA
+constexpr int kMelWarps = 4;  // contraction warps per CTA (mel kernel)
+constexpr int kMaxItems = 64;  // filter groups (of 8) per contraction
 constexpr int kMaxItemsPerWarp = 32;
-constexpr int kFragSmemSteps = 112;              // filterbank fragments kept in shared memory (x 512 B)
+constexpr int kFragSmemSteps = 112;  // filterbank fragments kept in shared memory (x 512 B)
+constexpr int kMaxSlots = 64;
 
-// The mel contraction D[16 frames][n_mels] = P[16][bins] * F[bins][n_mels] is cut into ITEMS:
-// (group of 8 filters) x (chunk of consecutive 8-bin k-steps where that group is non-zero).
-// Items are spread over the 8 warps by descending size; partial sums meet in shared memory and
-// are added in a fixed order, so results do not depend on scheduling.
+// Geometry of one transform size: G lanes per frame pair.
+template <int G>
+struct Geo {
+  static constexpr int kG = G;
+  static constexpr int kNfft = 32 * G;
+  static constexpr int kBins = kNfft / 2 + 1;
+  static constexpr int kGroups = 32 / G;        // frame pairs per warp
+  static constexpr int kFrames = 2 * kGroups;   // frames per warp and iteration ("unit")
+  static constexpr int kRowLd = G + 1;          // float2 pitch of one transpose row (bank-conflict free)
+  static constexpr int kRegion = 32 * (G + 1) + (G == 8 ? 8 : 0);  // float2 per lane group (skewed for G = 8)
+  static constexpr int kTileF2 = kGroups * kRegion;                // float2 per warp
+  static constexpr int kStageFloats = 2 * kTileF2;                 // a staged unit must fit the tile
+  static constexpr int kSlots = kWarps * kFrames;                  // frames finished per CTA iteration
+  static constexpr int kPitch = ((kBins + 7 - 4 + 31) / 32) * 32 + 4;  // floats per power row, == 4 (mod 32)
+  static constexpr int kLogG = G == 32 ? 5 : (G == 16 ? 4 : 3);
+};
+
+// The mel contraction D[16 frames][n_mels] = P[16][bins] * F[bins][n_mels] is cut into ITEMS =
+// groups of 8 filters with the k-steps where the group is non-zero, spread over the contraction warps
+// by descending size.
 struct MelItem {
   int tile;      // filter group: filters [8 tile, 8 tile + 8)
-  int kstart;    // first bin of the chunk (multiple of 8)
-  int nsteps;    // k-steps in the chunk
-  int frag_off;  // index of the chunk's first step in the fragment array
-};
-struct MelTile {
-  int part[4];  // item indices whose partial sums make up this filter group; kMaxItems == "all zero"
+  int kstart;    // first bin of the first k-step (multiple of 8)
+  int nsteps;    // k-steps
+  int frag_off;  // index of the first step in the fragment array
 };
 struct MelPlan {  // built on the device by prepare_mma_kernel
-  int n_tiles, n_items, total_steps, chunk;
+  int n_tiles, n_items, total_steps, pad;
   int warp_cnt[kWarps];
   int warp_items[kWarps][kMaxItemsPerWarp];
   MelItem items[kMaxItems];
-  MelTile tiles[64];
 };
 
 struct Pow2Extra {  // tables appended to the generic workspace
@@ -91,7 +98,9 @@ inline Pow2Extra pow2_layout(const b200a_frontend_desc& d, size_t base) {
   return e;
 }
 
-bool pow2_applicable(const b200a_frontend_desc& d) { return d.n_fft == kN && d.onesided != 0; }
+bool pow2_applicable(const b200a_frontend_desc& d) {
+  return (d.n_fft == 1024 || d.n_fft == 512 || d.n_fft == 256) && d.onesided != 0;
+}
 
 // ---- compile-time helpers -----------------------------------------------------------------
 template <int... Is, typename F>
@@ -105,6 +114,10 @@ __device__ __forceinline__ void static_for(F&& f) {
 
 __host__ __device__ constexpr int brev5(int v) {
   return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
+}
+template <int LOG>
+__host__ __device__ constexpr int brev(int v) {  // bit reversal of a LOG-bit index
+  return brev5(v) >> (5 - LOG);
 }
 
 // cos / sin of 2 pi k / 32, k = 0..16
@@ -150,27 +163,30 @@ __device__ __forceinline__ void bfly(float2& a, float2& b) {
   }
 }
 
-// In-register 32-point DFT.  Input a[brev5(j)] = x[j]; output a[k] = X[k] (natural order).
-__device__ __forceinline__ void fft32(float2 (&a)[32]) {
-  static_for<5>([&](auto si) {
-    constexpr int len = 2 << decltype(si)::value;  // 2, 4, 8, 16, 32
+// In-register LEN-point DFT on a[OFF .. OFF+LEN).  Input a[OFF + brev<log2 LEN>(j)] = x[j]; output
+// a[OFF + k] = X[k] (natural order).
+template <int LEN, int OFF>
+__device__ __forceinline__ void fft_regs(float2 (&a)[32]) {
+  constexpr int kStages = LEN == 32 ? 5 : (LEN == 16 ? 4 : 3);
+  static_for<kStages>([&](auto si) {
+    constexpr int len = 2 << decltype(si)::value;  // 2, 4, ..., LEN
     constexpr int half = len / 2;
-    static_for<16>([&](auto bi) {
+    static_for<LEN / 2>([&](auto bi) {
       constexpr int b = decltype(bi)::value;
       constexpr int i = (b / half) * len, j = b % half;
-      bfly<j*(32 / len)>(a[i + j], a[i + j + half]);
+      bfly<j*(32 / len)>(a[OFF + i + j], a[OFF + i + j + half]);
     });
   });
 }
 
 struct Pow2Params {
   const float* wave;
-  int64_t length, row_stride, frames, pairs_per_row, total_pairs;
+  int64_t length, row_stride, frames, units_per_row, total_units;
   float* out;
   float* group_max;
   int64_t rows_per_group;
-  const float* window;   // [1024] centre padded
-  const float2* tw2d;    // [32][32]  W_1024^(k2 * g) at [k2][g]
+  const float* window;   // [n_fft] centre padded
+  const float2* tw2d;    // [32][G]  W_nfft^(k2 * g) at [k2][g]
   const MelPlan* plan;
   const float4* frags;   // [steps][32] (b0_hi, b1_hi, b0_lo, b1_lo) in mma B-fragment order
   const WsHeader* hdr;
@@ -226,69 +242,82 @@ __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
-// Per-warp walker over this warp's pairs: (row, pair-in-row) of the current and the next pair,
+// Per-warp walker over this warp's units: (row, unit-in-row) of the current and the next unit,
 // advanced without divisions.
-struct PairCursor {
-  int64_t u, stride, step_rows, step_pairs, ppr;
-  int64_t row, pr, nrow, npr;
-  __device__ __forceinline__ void init(int64_t first, int64_t stride_, int64_t pairs_per_row) {
+struct UnitCursor {
+  int64_t u, stride, step_rows, step_units, upr;
+  int64_t row, ub, nrow, nub;
+  __device__ __forceinline__ void init(int64_t first, int64_t stride_, int64_t units_per_row) {
     u = first;
     stride = stride_;
-    ppr = pairs_per_row;
-    step_rows = stride / ppr;
-    step_pairs = stride - step_rows * ppr;
-    row = first / ppr;
-    pr = first - row * ppr;
+    upr = units_per_row;
+    step_rows = stride / upr;
+    step_units = stride - step_rows * upr;
+    row = first / upr;
+    ub = first - row * upr;
     nrow = row + step_rows;
-    npr = pr + step_pairs;
-    if (npr >= ppr) { npr -= ppr; ++nrow; }
+    nub = ub + step_units;
+    if (nub >= upr) { nub -= upr; ++nrow; }
   }
   __device__ __forceinline__ void advance() {
     u += stride;
     row = nrow;
-    pr = npr;
+    ub = nub;
     nrow += step_rows;
-    npr += step_pairs;
-    if (npr >= ppr) { npr -= ppr; ++nrow; }
+    nub += step_units;
+    if (nub >= upr) { nub -= upr; ++nrow; }
   }
 };
 
-// a pair can be staged by one bulk copy iff both frames exist and lie inside the row un-padded
-__device__ __forceinline__ bool bulk_eligible(const Pow2Params& p, int half, int64_t u, int64_t pr) {
-  if (!p.bulk_ok || u >= p.total_pairs) return false;
-  const int64_t sa = 2 * pr * p.hop - half - p.pad;
-  return 2 * pr + 1 < p.frames && sa >= 0 && sa + p.hop + kN <= p.length;
+// a unit can be staged by one bulk copy iff all its frames exist and lie inside the row un-padded
+template <int G>
+__device__ __forceinline__ bool bulk_eligible(const Pow2Params& p, int half, int64_t u, int64_t ub) {
+  using Ge = Geo<G>;
+  if (!p.bulk_ok || u >= p.total_units) return false;
+  const int64_t t0 = ub * Ge::kFrames;
+  const int64_t s0 = t0 * p.hop - half - p.pad;
+  return t0 + Ge::kFrames <= p.frames && s0 >= 0 && s0 + (int64_t)(Ge::kFrames - 1) * p.hop + Ge::kNfft <= p.length;
 }
-__device__ __forceinline__ void issue_bulk(const Pow2Params& p, int half, int64_t row, int64_t pr, void* dst,
+template <int G>
+__device__ __forceinline__ void issue_bulk(const Pow2Params& p, int half, int64_t row, int64_t ub, void* dst,
                                            uint64_t* bar) {
-  const float* src = p.wave + row * p.row_stride + (2 * pr * p.hop - half - p.pad);
-  const uint32_t bytes = (uint32_t)(kN + p.hop) * 4u;
+  using Ge = Geo<G>;
+  const float* src = p.wave + row * p.row_stride + (ub * Ge::kFrames * p.hop - half - p.pad);
+  const uint32_t bytes = (uint32_t)(Ge::kNfft + (Ge::kFrames - 1) * p.hop) * 4u;
   mbar_expect_tx(bar, bytes);
   bulk_g2s(dst, src, bytes, bar);
 }
 
-// One warp, one pair of frames: samples -> windowed complex signal -> 1024-point FFT -> the two power
-// spectra.  On return lane l holds bins k = l + 32 k1 in pa[k1] / pb[k1] (k1 < 16) and lane 0 bin 512 in [16].
-//   stage      where a prefetched pair was staged (may alias `tile` when STAGE_IS_TILE)
-//   STAGE_IS_TILE  the staging buffer is the transpose tile itself: the NEXT pair's bulk copy is issued
+// One warp, one unit (32/G frame pairs): samples -> windowed complex signals -> n_fft-point FFTs -> the
+// power spectra.  On return lane (group gi, l) holds bins k = l + G m in pa[m] / pb[m] (m < 16) of frames
+// t0 + 2 gi and t0 + 2 gi + 1, and lanes with l == 0 bin n_fft/2 in [16].
+//   stage      where a prefetched unit was staged (aliases `tile` when STAGE_IS_TILE)
+//   STAGE_IS_TILE  the staging buffer is the transpose tile itself: the NEXT unit's bulk copy is issued
 //                  only after pass 2 has read the tile back
-template <int POWER_MODE, int HG, bool STAGE_IS_TILE>
-__device__ __forceinline__ void transform_pair(const Pow2Params& p, const float (&wreg)[32], const float2* s_tw,
+template <int POWER_MODE, int G, int HG, bool STAGE_IS_TILE>
+__device__ __forceinline__ void transform_unit(const Pow2Params& p, const float (&wreg)[32], const float2* s_tw,
                                                float2* tile, float* stage, uint64_t* bar, uint32_t& parity,
-                                               bool& staged, const PairCursor& cur, int half, int lane,
+                                               bool& staged, const UnitCursor& cur, int half, int lane,
                                                float (&pa)[17], float (&pb)[17]) {
-  const int64_t row = cur.row, ta = 2 * cur.pr, tb = ta + 1;
-  const bool has_b = tb < p.frames;
+  using Ge = Geo<G>;
+  const int gi = lane / G, l = lane % G;
+  const int64_t row = cur.row, t0 = cur.ub * Ge::kFrames;
+  const int64_t ta = t0 + 2 * gi, tb = ta + 1;
+  const bool has_a = ta < p.frames, has_b = tb < p.frames;
   const float* __restrict__ x = p.wave + row * p.row_stride;
-  const int64_t sa = ta * p.hop - half - p.pad;  // first raw sample of frame a
-  const int64_t sb = sa + p.hop;
-  const bool next_staged = bulk_eligible(p, half, cur.u + cur.stride, cur.npr);
+  const int64_t s0 = t0 * p.hop - half - p.pad;  // first raw sample of the unit
+  const int64_t sa = s0 + (int64_t)2 * gi * p.hop, sb = sa + p.hop;
+  const bool next_staged = bulk_eligible<G>(p, half, cur.u + cur.stride, cur.nub);
+  // every frame of the unit inside the signal: plain loads; otherwise the padding-aware gather
+  const int64_t last = p.frames - t0 < Ge::kFrames ? p.frames - t0 : Ge::kFrames;  // frames present
+  const bool interior = s0 >= 0 && s0 + (last - 1) * p.hop + Ge::kNfft <= p.length;
 
   float2 a[32];
+  float2* grp_tile = tile + gi * Ge::kRegion;
   if (staged) {
     mbar_wait(bar, parity);
     parity ^= 1;
-    if constexpr (HG >= 0) {
+    if constexpr (HG >= 0) {  // G == 32: frame b is frame a shifted by HG lane-rows
       constexpr int kV = 32 + (HG >= 0 ? HG : 0);
       float v[kV];
       static_for<kV>([&](auto ji) {
@@ -300,171 +329,185 @@ __device__ __forceinline__ void transform_pair(const Pow2Params& p, const float 
         a[brev5(j)] = make_float2(v[j] * wreg[j], v[j + (HG >= 0 ? HG : 0)] * wreg[j]);
       });
     } else {
-      const float* sb_ptr = stage + p.hop;
+      const float* pa_ptr = stage + 2 * gi * p.hop + l;
+      const float* pb_ptr = pa_ptr + p.hop;
       static_for<32>([&](auto ji) {
         constexpr int j = decltype(ji)::value;
-        a[brev5(j)] = make_float2(stage[lane + 32 * j] * wreg[j], sb_ptr[lane + 32 * j] * wreg[j]);
+        a[brev5(j)] = make_float2(pa_ptr[G * j] * wreg[j], pb_ptr[G * j] * wreg[j]);
       });
     }
     __syncwarp();  // every lane has consumed the staging buffer
-  } else if (sa >= 0 && (has_b ? sb : sa) + kN <= p.length) {
+  } else if (interior) {
     static_for<32>([&](auto ji) {
       constexpr int j = decltype(ji)::value;
-      const float va = __ldg(x + sa + lane + 32 * j);
-      const float vb = has_b ? __ldg(x + sb + lane + 32 * j) : 0.f;
+      const float va = has_a ? __ldg(x + sa + l + G * j) : 0.f;
+      const float vb = has_b ? __ldg(x + sb + l + G * j) : 0.f;
       a[brev5(j)] = make_float2(va * wreg[j], vb * wreg[j]);
     });
   } else {
-    // edge pair (padding / reflection / ragged end): gather through the warp's tile with a
+    // edge unit (padding / reflection / ragged end): gather through the group's tile region with a
     // rolled loop so the index arithmetic is not replicated 64 times in the instruction stream
 #pragma unroll 1
     for (int j = 0; j < 32; ++j) {
-      const int n = lane + 32 * j;
-      const int64_t ia = source_index(ta * p.hop + n, p.length, p.pad, half, p.pad_mode);
+      const int n = l + G * j;
+      const int64_t ia = has_a ? source_index(ta * p.hop + n, p.length, p.pad, half, p.pad_mode) : -1;
       const int64_t ib = has_b ? source_index(tb * p.hop + n, p.length, p.pad, half, p.pad_mode) : -1;
-      tile[n] = make_float2(ia >= 0 ? __ldg(x + ia) : 0.f, ib >= 0 ? __ldg(x + ib) : 0.f);
+      grp_tile[n] = make_float2(ia >= 0 ? __ldg(x + ia) : 0.f, ib >= 0 ? __ldg(x + ib) : 0.f);
     }
     __syncwarp();
     static_for<32>([&](auto ji) {
       constexpr int j = decltype(ji)::value;
-      const float2 v = tile[lane + 32 * j];
+      const float2 v = grp_tile[l + G * j];
       a[brev5(j)] = make_float2(v.x * wreg[j], v.y * wreg[j]);
     });
     __syncwarp();
   }
   if constexpr (!STAGE_IS_TILE) {  // separate staging buffer: prefetch right away
     staged = next_staged;
-    if (staged && lane == 0) issue_bulk(p, half, cur.nrow, cur.npr, stage, bar);
+    if (staged && lane == 0) issue_bulk<G>(p, half, cur.nrow, cur.nub, stage, bar);
   }
 
-  fft32(a);  // a[k2] = Y[lane][k2]
+  fft_regs<32, 0>(a);  // a[k2] = Y[l][k2]
 
-  // twiddle + transpose: element (g = lane, k2) -> tile[k2][g]
-  tile[lane] = a[0];
+  // twiddle + transpose inside the lane group: element (l, k2) -> region[k2][l]
+  grp_tile[l] = a[0];
   static_for<31>([&](auto ki) {
     constexpr int k2 = decltype(ki)::value + 1;
-    const float2 w = s_tw[k2 * 32 + lane];
+    const float2 w = s_tw[k2 * G + l];
     const float2 v = a[k2];
-    tile[k2 * kTileLd + lane] = make_float2(fmaf(v.x, w.x, -v.y * w.y), fmaf(v.x, w.y, v.y * w.x));
+    grp_tile[k2 * Ge::kRowLd + l] = make_float2(fmaf(v.x, w.x, -v.y * w.y), fmaf(v.x, w.y, v.y * w.x));
   });
   __syncwarp();
-  static_for<32>([&](auto gi) {
-    constexpr int g = decltype(gi)::value;
-    a[brev5(g)] = tile[lane * kTileLd + g];
+  // lane l now owns k2 = l + G q, q < 32/G: slot q*G + brev(g) <- element (g, l + G q)
+  static_for<32>([&](auto si) {
+    constexpr int s = decltype(si)::value;
+    constexpr int q = s / G, g = s % G;
+    a[q * G + brev<Ge::kLogG>(g)] = grp_tile[(l + G * q) * Ge::kRowLd + g];
   });
   __syncwarp();
-  if constexpr (STAGE_IS_TILE) {  // the tile is free until the next pair's transpose: stage into it
+  if constexpr (STAGE_IS_TILE) {  // the tile is free until the next unit's transpose: stage into it
     staged = next_staged;
     if (staged && lane == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads above -> async write
-      issue_bulk(p, half, cur.nrow, cur.npr, stage, bar);
+      issue_bulk<G>(p, half, cur.nrow, cur.nub, stage, bar);
     }
   }
 
-  fft32(a);  // a[k1] = Z[lane + 32 k1]
+  static_for<Ge::kGroups>([&](auto qi) { fft_regs<G, decltype(qi)::value * G>(a); });
+  // a[q*G + k1] = Z[(l + G q) + 32 k1]; bin k = l + G m with m = q + (32/G) k1  <->  slot (m % NG)*G + m / NG
 
-  // ---- un-pack the two spectra: need Z[N - k], k = lane + 32 k1, k1 = 0..15 (+ bin 512 on lane 0)
-  const int src = (32 - lane) & 31;
-  static_for<16>([&](auto ki) {
-    constexpr int k1 = decltype(ki)::value;
-    // lanes >= 1: Z[N-k] = Z[(32-lane) + 32 (31-k1)] sits on lane `src`, slot 31-k1
-    float mr = __shfl_sync(0xffffffffu, a[31 - k1].x, src);
-    float mi = __shfl_sync(0xffffffffu, a[31 - k1].y, src);
-    if (lane == 0) {  // lane 0: Z[N-k] = Z[32 (32-k1)] is its own slot 32-k1 (slot 0 for k1 = 0)
-      mr = a[(32 - k1) & 31].x;
-      mi = a[(32 - k1) & 31].y;
+  // ---- un-pack the two spectra: need Z[N - k] for k = l + G m, m = 0..15 (+ bin N/2 on l == 0) ----
+  constexpr int NG = Ge::kGroups;
+  const int src = (lane & ~(G - 1)) | ((G - l) & (G - 1));
+  static_for<16>([&](auto mi) {
+    constexpr int m = decltype(mi)::value;
+    constexpr int slot = (m % NG) * G + m / NG;
+    // l >= 1: N - k = (G - l) + G (31 - m): on lane `src`, slot of m' = 31 - m
+    constexpr int mm = 31 - m, mslot = (mm % NG) * G + mm / NG;
+    float mr = __shfl_sync(0xffffffffu, a[mslot].x, src);
+    float mi_ = __shfl_sync(0xffffffffu, a[mslot].y, src);
+    if (l == 0) {  // l == 0: N - k = G (32 - m): own slot of m' = 32 - m (slot 0 for m = 0)
+      constexpr int m0 = (32 - m) & 31, slot0 = (m0 % NG) * G + m0 / NG;
+      mr = a[slot0].x;
+      mi_ = a[slot0].y;
     }
-    const float zr = a[k1].x, zi = a[k1].y;
-    pa[k1] = pow_of<POWER_MODE>(zr + mr, zi - mi, p.power);
-    pb[k1] = pow_of<POWER_MODE>(zi + mi, mr - zr, p.power);
+    const float zr = a[slot].x, zi = a[slot].y;
+    pa[m] = pow_of<POWER_MODE>(zr + mr, zi - mi_, p.power);
+    pb[m] = pow_of<POWER_MODE>(zi + mi_, mr - zr, p.power);
   });
-  // bin 512 (lane 0, slot 16) is its own mirror: A = Re, B = Im  (x2 because wreg carries the 1/2)
-  pa[16] = pow_of<POWER_MODE>(2.f * a[16].x, 0.f, p.power);
-  pb[16] = pow_of<POWER_MODE>(2.f * a[16].y, 0.f, p.power);
+  // bin N/2 (l == 0, m = 16) is its own mirror: A = Re, B = Im  (x2 because wreg carries the 1/2)
+  constexpr int slot16 = (16 % NG) * G + 16 / NG;
+  pa[16] = pow_of<POWER_MODE>(2.f * a[slot16].x, 0.f, p.power);
+  pb[16] = pow_of<POWER_MODE>(2.f * a[slot16].y, 0.f, p.power);
 }
 
+template <int G>
 __device__ __forceinline__ void load_window(const Pow2Params& p, int lane, float (&wreg)[32]) {
-  // window (x 1/2 from the un-packing, x the normalisation scale) for n = lane + 32 j
+  // window (x 1/2 from the un-packing, x the normalisation scale) for n = l + G j
   const float hs = 0.5f * p.hdr->scale;
+  const int l = lane % G;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) wreg[j] = p.window[lane + 32 * j] * hs;
+  for (int j = 0; j < 32; ++j) wreg[j] = p.window[l + G * j] * hs;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Spectrogram kernel: 8 independent warps, power spectra straight to global memory.
 // ------------------------------------------------------------------------------------------------
-template <int POWER_MODE, int HG>
-__global__ void __launch_bounds__(kWarps * 32, 1) stft1024_power_kernel(const Pow2Params p) {
+template <int POWER_MODE, int G, int HG>
+__global__ void __launch_bounds__(kWarps * 32, 1) stft_pow2_power_kernel(const Pow2Params p) {
+  using Ge = Geo<G>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2* s_tw = reinterpret_cast<float2*>(smem_raw);                                 // [32][32]
-  float2* s_tile_all = s_tw + 32 * 32;                                                // [kWarps][32 * 33]
-  float* s_stage_all = reinterpret_cast<float*>(s_tile_all + kWarps * kTileFloat2);   // [kWarps][kStageFloats]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage_all + kWarps * kStageFloats);  // [kWarps]
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);                                    // [32][G]
+  float2* s_tile_all = s_tw + 32 * 32;                                                   // [kWarps][kTileF2]
+  float* s_stage_all = reinterpret_cast<float*>(s_tile_all + kWarps * Ge::kTileF2);      // [kWarps][kStageFloats]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage_all + kWarps * Ge::kStageFloats);  // [kWarps]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 32 * 32; i += blockDim.x) s_tw[i] = p.tw2d[i];
+  for (int i = tid; i < 32 * G; i += blockDim.x) s_tw[i] = p.tw2d[i];
   if (tid < kWarps) mbar_init(s_bar + tid, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
-  float2* tile = s_tile_all + warp * kTileFloat2;
-  float* stage = s_stage_all + warp * kStageFloats;
+  float2* tile = s_tile_all + warp * Ge::kTileF2;
+  float* stage = s_stage_all + warp * Ge::kStageFloats;
   uint64_t* bar = s_bar + warp;
   float wreg[32];
-  load_window(p, lane, wreg);
-  const int half = p.center ? kN / 2 : 0;
+  load_window<G>(p, lane, wreg);
+  const int half = p.center ? Ge::kNfft / 2 : 0;
+  const int gi = lane / G, l = lane % G;
   uint32_t parity = 0;
   bool staged = false;
-  PairCursor cur;
-  cur.init((int64_t)blockIdx.x * kWarps + warp, (int64_t)gridDim.x * kWarps, p.pairs_per_row);
-  if (bulk_eligible(p, half, cur.u, cur.pr)) {
-    if (lane == 0) issue_bulk(p, half, cur.row, cur.pr, stage, bar);
+  UnitCursor cur;
+  cur.init((int64_t)blockIdx.x * kWarps + warp, (int64_t)gridDim.x * kWarps, p.units_per_row);
+  if (bulk_eligible<G>(p, half, cur.u, cur.ub)) {
+    if (lane == 0) issue_bulk<G>(p, half, cur.row, cur.ub, stage, bar);
     staged = true;
   }
-  for (; cur.u < p.total_pairs; cur.advance()) {
+  for (; cur.u < p.total_units; cur.advance()) {
     float pa[17], pb[17];
-    transform_pair<POWER_MODE, HG, false>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa, pb);
-    const int64_t ta = 2 * cur.pr;
-    const bool has_b = ta + 1 < p.frames;
-    float* oa = p.out + (cur.row * p.frames + ta) * kBins;
-    float* ob = oa + kBins;
+    transform_unit<POWER_MODE, G, HG, false>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa, pb);
+    const int64_t ta = cur.ub * Ge::kFrames + 2 * gi;
+    const bool has_a = ta < p.frames, has_b = ta + 1 < p.frames;
+    float* oa = p.out + (cur.row * p.frames + ta) * Ge::kBins;
+    float* ob = oa + Ge::kBins;
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) {
-      oa[lane + 32 * k1] = pa[k1];
-      if (has_b) ob[lane + 32 * k1] = pb[k1];
+    for (int m = 0; m < 16; ++m) {
+      if (has_a) oa[l + G * m] = pa[m];
+      if (has_b) ob[l + G * m] = pb[m];
     }
-    if (lane == 0) {
-      oa[512] = pa[16];
-      if (has_b) ob[512] = pb[16];
+    if (l == 0) {
+      if (has_a) oa[Ge::kNfft / 2] = pa[16];
+      if (has_b) ob[Ge::kNfft / 2] = pb[16];
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Mel / MFCC-feature kernel, warp specialised: warps 0-7 transform (one frame pair each per iteration)
-// and publish power rows into a double-buffered shared tile; warps 8-11 contract each finished tile of
-// 16 frames with the filterbank on the tensor pipe and store the features.  The two groups only meet at
-// the tile's full/empty mbarriers, so the FFT warps never wait for the contraction.
+// Mel / MFCC-feature kernel, warp specialised: warps 0-7 transform (one unit each per iteration)
+// and publish power rows into a double-buffered shared tile; warps 8-11 contract each finished tile
+// (16, 32 or 64 frames) with the filterbank on the tensor pipe and store the features.  The two groups
+// only meet at the tile's full/empty mbarriers, so the FFT warps never wait for the contraction.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMelWarps = 4;
 constexpr int kFftRegs = 200, kMelRegs = 96;  // 256*200 + 128*96 = 63488 <= 64512 = 384 * 168
 
-template <int POWER_MODE, int HG>
-__global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft1024_mel_kernel(const Pow2Params p) {
+template <int POWER_MODE, int G, int HG>
+__global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft_pow2_mel_kernel(const Pow2Params p) {
+  using Ge = Geo<G>;
+  constexpr int kSlots = Ge::kSlots, kPitch = Ge::kPitch;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2* s_tw = reinterpret_cast<float2*>(smem_raw);                          // [32][32]
-  float2* s_tile_all = s_tw + 32 * 32;                                         // [kWarps][32 * 33] (also staging)
-  float* s_pow = reinterpret_cast<float*>(s_tile_all + kWarps * kTileFloat2);  // [2][kSlots][kPowPitch]
-  int64_t* s_slot = reinterpret_cast<int64_t*>(s_pow + 2 * kSlots * kPowPitch);  // [2][kSlots] out offsets
-  int64_t* s_grp = s_slot + 2 * kSlots;                                        // [2][kSlots] top_db group
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + 2 * kSlots);           // [kWarps] staging, [2] full, [2] empty
-  uint64_t* s_full = s_bar + kWarps;
-  uint64_t* s_empty = s_full + 2;
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);                              // [32][G]
+  float2* s_tile_all = s_tw + 32 * 32;                                             // [kWarps][kTileF2] (also staging)
+  float* s_pow = reinterpret_cast<float*>(s_tile_all + kWarps * Ge::kTileF2);      // [2][kSlots][kPitch]
+  int64_t* s_slot = reinterpret_cast<int64_t*>(s_pow + 2 * kSlots * kPitch);        // [2][kSlots] out offsets
+  int64_t* s_grp = s_slot + 2 * kSlots;                                            // [2][kSlots] top_db group
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + 2 * kSlots);               // [kWarps] staging
+  uint64_t* s_full = s_bar + kWarps;                                               // [2]
+  uint64_t* s_empty = s_full + 2;                                                  // [2]
   MelPlan* s_plan = reinterpret_cast<MelPlan*>(s_empty + 2);
-  float4* s_frags = reinterpret_cast<float4*>(s_plan + 1);                     // [<= kFragSmemSteps][32]
+  float4* s_frags = reinterpret_cast<float4*>(s_plan + 1);                         // [<= kFragSmemSteps][32]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 32 * 32; i += blockDim.x) s_tw[i] = p.tw2d[i];
+  for (int i = tid; i < 32 * G; i += blockDim.x) s_tw[i] = p.tw2d[i];
   {
     const int* src = reinterpret_cast<const int*>(p.plan);
     int* dst = reinterpret_cast<int*>(s_plan);
@@ -474,10 +517,10 @@ __global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft1024_mel_ker
   const bool frags_in_smem = total_steps <= kFragSmemSteps;
   if (frags_in_smem)
     for (int i = tid; i < total_steps * 32; i += blockDim.x) s_frags[i] = p.frags[i];
-  // columns >= 513 of every power row are read by the last k-step: keep them finite (zero)
-  for (int i = tid; i < 2 * kSlots * (kPowPitch - kBins); i += blockDim.x) {
-    const int r = i / (kPowPitch - kBins), c = i - r * (kPowPitch - kBins);
-    s_pow[r * kPowPitch + kBins + c] = 0.f;
+  // columns >= n_bins of every power row are read by the last k-step: keep them finite (zero)
+  for (int i = tid; i < 2 * kSlots * (kPitch - Ge::kBins); i += blockDim.x) {
+    const int r = i / (kPitch - Ge::kBins), c = i - r * (kPitch - Ge::kBins);
+    s_pow[r * kPitch + Ge::kBins + c] = 0.f;
   }
   if (tid < kWarps) mbar_init(s_bar + tid, 1);
   if (tid == 0) {
@@ -496,49 +539,52 @@ __global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft1024_mel_ker
   if (warp < kWarps) {
     // =============================== transform warps ===========================================
     reg_alloc<kFftRegs>();
-    float2* tile = s_tile_all + warp * kTileFloat2;
+    float2* tile = s_tile_all + warp * Ge::kTileF2;
     float* stage = reinterpret_cast<float*>(tile);
     uint64_t* bar = s_bar + warp;
     float wreg[32];
-    load_window(p, lane, wreg);
-    const int half = p.center ? kN / 2 : 0;
+    load_window<G>(p, lane, wreg);
+    const int half = p.center ? Ge::kNfft / 2 : 0;
+    const int gi = lane / G, l = lane % G;
     uint32_t parity = 0;
     bool staged = false;
-    PairCursor cur;
-    cur.init(u0 + warp, stride, p.pairs_per_row);
-    if (bulk_eligible(p, half, cur.u, cur.pr)) {
-      if (lane == 0) issue_bulk(p, half, cur.row, cur.pr, stage, bar);
+    UnitCursor cur;
+    cur.init(u0 + warp, stride, p.units_per_row);
+    if (bulk_eligible<G>(p, half, cur.u, cur.ub)) {
+      if (lane == 0) issue_bulk<G>(p, half, cur.row, cur.ub, stage, bar);
       staged = true;
     }
     int it = 0;
-    for (int64_t base = u0; base < p.total_pairs; base += stride, ++it, cur.advance()) {
-      const bool valid = cur.u < p.total_pairs;
+    for (int64_t base = u0; base < p.total_units; base += stride, ++it, cur.advance()) {
+      const bool valid = cur.u < p.total_units;
       float pa[17], pb[17];
       if (valid)
-        transform_pair<POWER_MODE, HG, true>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa, pb);
+        transform_unit<POWER_MODE, G, HG, true>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
+                                                pb);
       const int b = it & 1;
       if (it >= 2) mbar_wait(s_empty + b, ((it >> 1) & 1) ^ 1);  // the mel warps have drained this buffer
-      float* prow_a = s_pow + (size_t)(b * kSlots + 2 * warp) * kPowPitch;
-      float* prow_b = prow_a + kPowPitch;
+      const int slot_a = Ge::kFrames * warp + 2 * gi;
+      float* prow_a = s_pow + (size_t)(b * kSlots + slot_a) * kPitch;
+      float* prow_b = prow_a + kPitch;
       if (valid) {
 #pragma unroll
-        for (int k1 = 0; k1 < 16; ++k1) {
-          prow_a[lane + 32 * k1] = pa[k1];
-          prow_b[lane + 32 * k1] = pb[k1];
+        for (int m = 0; m < 16; ++m) {
+          prow_a[l + G * m] = pa[m];
+          prow_b[l + G * m] = pb[m];
         }
-        if (lane == 0) {
-          prow_a[512] = pa[16];
-          prow_b[512] = pb[16];
+        if (l == 0) {
+          prow_a[Ge::kNfft / 2] = pa[16];
+          prow_b[Ge::kNfft / 2] = pb[16];
         }
       }
-      if (lane == 0) {
-        const int64_t ta = 2 * cur.pr;
-        const int64_t oa = valid ? (cur.row * p.frames + ta) * (int64_t)width : -1;
-        s_slot[b * kSlots + 2 * warp] = oa;
-        s_slot[b * kSlots + 2 * warp + 1] = (valid && ta + 1 < p.frames) ? oa + width : -1;
+      if (l == 0) {
+        const int64_t ta = cur.ub * Ge::kFrames + 2 * gi;
+        const int64_t oa = (cur.row * p.frames + ta) * (int64_t)width;
+        s_slot[b * kSlots + slot_a] = (valid && ta < p.frames) ? oa : -1;
+        s_slot[b * kSlots + slot_a + 1] = (valid && ta + 1 < p.frames) ? oa + width : -1;
         const int64_t g = cur.row / p.rows_per_group;
-        s_grp[b * kSlots + 2 * warp] = g;
-        s_grp[b * kSlots + 2 * warp + 1] = g;
+        s_grp[b * kSlots + slot_a] = g;
+        s_grp[b * kSlots + slot_a + 1] = g;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(s_full + b);
@@ -551,57 +597,67 @@ __global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft1024_mel_ker
     const int r = lane >> 2, c = lane & 3;
     const int cnt = s_plan->warp_cnt[mw];
     int it = 0;
-    for (int64_t base = u0; base < p.total_pairs; base += stride, ++it) {
+    for (int64_t base = u0; base < p.total_units; base += stride, ++it) {
       const int b = it & 1;
       mbar_wait(s_full + b, (it >> 1) & 1);
-      const float* pw = s_pow + (size_t)b * kSlots * kPowPitch;
-      const int64_t o_lo = s_slot[b * kSlots + r], o_hi = s_slot[b * kSlots + r + 8];
-      const int64_t g_lo = s_grp[b * kSlots + r], g_hi = s_grp[b * kSlots + r + 8];
-      for (int ii = 0; ii < cnt; ++ii) {
-        const MelItem mi = s_plan->items[s_plan->warp_items[mw][ii]];
-        const float* a_lo_row = pw + (size_t)r * kPowPitch + mi.kstart + c;
-        const float* a_hi_row = a_lo_row + 8 * kPowPitch;
-        // three independent accumulator chains (hi*hi, lo*hi, hi*lo), summed in a fixed order
-        float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
-        auto contract = [&](auto in_smem) {
-          const float4* fr = (decltype(in_smem)::value ? s_frags : p.frags) + (size_t)mi.frag_off * 32 + lane;
+#pragma unroll 1
+      for (int mt = 0; mt < kSlots / 16; ++mt) {  // 16-frame MMA tiles of this iteration
+        const float* pw = s_pow + (size_t)(b * kSlots + 16 * mt) * kPitch;
+        const int64_t o_lo = s_slot[b * kSlots + 16 * mt + r], o_hi = s_slot[b * kSlots + 16 * mt + r + 8];
+        const int64_t g_lo = s_grp[b * kSlots + 16 * mt + r], g_hi = s_grp[b * kSlots + 16 * mt + r + 8];
+        for (int ii = 0; ii < cnt; ++ii) {
+          const MelItem mi = s_plan->items[s_plan->warp_items[mw][ii]];
+          const float* a_lo_row = pw + (size_t)r * kPitch + mi.kstart + c;
+          const float* a_hi_row = a_lo_row + 8 * kPitch;
+          // three independent accumulator chains (hi*hi, lo*hi, hi*lo), summed in a fixed order
+          float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+          auto contract = [&](auto in_smem) {
+            const float4* fr = (decltype(in_smem)::value ? s_frags : p.frags) + (size_t)mi.frag_off * 32 + lane;
 #pragma unroll 4
-          for (int s = 0; s < mi.nsteps; ++s) {
-            float4 bf;
-            if constexpr (decltype(in_smem)::value) bf = fr[(size_t)s * 32];
-            else bf = __ldg(fr + (size_t)s * 32);
-            const float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
-            uint32_t hi[4], lo[4];
+            for (int s = 0; s < mi.nsteps; ++s) {
+              float4 bf;
+              if constexpr (decltype(in_smem)::value) bf = fr[(size_t)s * 32];
+              else bf = __ldg(fr + (size_t)s * 32);
+              const float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
+              uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) split_tf32(av[q], hi[q], lo[q]);
-            mma_tf32(d0, hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
-            mma_tf32(d1, lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
-            mma_tf32(d2, hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
+              for (int q = 0; q < 4; ++q) split_tf32(av[q], hi[q], lo[q]);
+              mma_tf32(d0, hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
+              mma_tf32(d1, lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
+              mma_tf32(d2, hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
+            }
+          };
+          if (frags_in_smem) contract(std::true_type{});
+          else contract(std::false_type{});
+          float d[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d[q] = d0[q] + (d1[q] + d2[q]);
+          const int n0 = 8 * mi.tile + 2 * c;
+          const bool n0_ok = n0 < p.n_mels, n1_ok = n0 + 1 < p.n_mels;
+          if (p.stage == B200A_STAGE_FEAT) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              d[q] = p.log_mels ? logf(d[q] + 1e-6f) : p.db_mult * log10f(fmaxf(d[q], p.db_amin)) - p.db_offset;
+            const float m_lo = fmaxf(n0_ok ? d[0] : -CUDART_INF_F, n1_ok ? d[1] : -CUDART_INF_F);
+            const float m_hi = fmaxf(n0_ok ? d[2] : -CUDART_INF_F, n1_ok ? d[3] : -CUDART_INF_F);
+            gmax.add(g_lo, m_lo, o_lo >= 0);
+            gmax.add(g_hi, m_hi, o_hi >= 0);
           }
-        };
-        if (frags_in_smem) contract(std::true_type{});
-        else contract(std::false_type{});
-        float d[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) d[q] = d0[q] + (d1[q] + d2[q]);
-        const int n0 = 8 * mi.tile + 2 * c;
-        const bool n0_ok = n0 < p.n_mels, n1_ok = n0 + 1 < p.n_mels;
-        if (p.stage == B200A_STAGE_FEAT) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            d[q] = p.log_mels ? logf(d[q] + 1e-6f) : p.db_mult * log10f(fmaxf(d[q], p.db_amin)) - p.db_offset;
-          const float m_lo = fmaxf(n0_ok ? d[0] : -CUDART_INF_F, n1_ok ? d[1] : -CUDART_INF_F);
-          const float m_hi = fmaxf(n0_ok ? d[2] : -CUDART_INF_F, n1_ok ? d[3] : -CUDART_INF_F);
-          gmax.add(g_lo, m_lo, o_lo >= 0);
-          gmax.add(g_hi, m_hi, o_hi >= 0);
-        }
-        if (o_lo >= 0) {
-          if (n1_ok) *reinterpret_cast<float2*>(p.out + o_lo + n0) = make_float2(d[0], d[1]);
-          else if (n0_ok) p.out[o_lo + n0] = d[0];
-        }
-        if (o_hi >= 0) {
-          if (n1_ok) *reinterpret_cast<float2*>(p.out + o_hi + n0) = make_float2(d[2], d[3]);
-          else if (n0_ok) p.out[o_hi + n0] = d[2];
+          const bool vec = n1_ok && (width & 1) == 0;  // 8-byte aligned pair
+          if (o_lo >= 0) {
+            if (vec) *reinterpret_cast<float2*>(p.out + o_lo + n0) = make_float2(d[0], d[1]);
+            else {
+              if (n0_ok) p.out[o_lo + n0] = d[0];
+              if (n1_ok) p.out[o_lo + n0 + 1] = d[1];
+            }
+          }
+          if (o_hi >= 0) {
+            if (vec) *reinterpret_cast<float2*>(p.out + o_hi + n0) = make_float2(d[2], d[3]);
+            else {
+              if (n0_ok) p.out[o_hi + n0] = d[2];
+              if (n1_ok) p.out[o_hi + n0 + 1] = d[3];
+            }
+          }
         }
       }
       __syncwarp();
@@ -612,22 +668,22 @@ __global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft1024_mel_ker
 }
 
 // ---- table preparation ------------------------------------------------------------------------
-__global__ void prepare_tw2d_kernel(float2* tw2d) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = k2 * 32 + g
-  if (i < 32 * 32) {
-    const int k2 = i >> 5, g = i & 31;
+__global__ void prepare_tw2d_kernel(float2* tw2d, int G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = k2 * G + g
+  if (i < 32 * G) {
+    const int k2 = i / G, g = i - k2 * G;
     double s, c;
-    sincospi(-2.0 * (double)(k2 * g) / (double)kN, &s, &c);
+    sincospi(-2.0 * (double)(k2 * g) / (double)(32 * G), &s, &c);
     tw2d[i] = make_float2((float)c, (float)s);
   }
 }
 
 // Builds the mel contraction plan: per group of 8 filters the 8-bin k-steps its non-zero bins span,
-// cut into chunks (items), spread over the warps by descending size; and the filterbank values split
+// groups spread over the contraction warps by descending size; and the filterbank values split
 // into TF32 hi/lo parts in mma.m16n8k8 B-fragment order.
 __global__ void prepare_mma_kernel(const float* __restrict__ fb, const int2* __restrict__ bands, int n_bins, int n_mels,
                                    int n_tiles, MelPlan* plan, float4* frags) {
-  __shared__ int t_kstart[64], t_steps[64];
+  __shared__ int t_kstart[kMaxItems], t_steps[kMaxItems];
   if (threadIdx.x == 0) {
     int total = 0;
     for (int t = 0; t < n_tiles; ++t) {
@@ -638,42 +694,28 @@ __global__ void prepare_mma_kernel(const float* __restrict__ fb, const int2* __r
       }
       t_kstart[t] = hi > lo ? (lo & ~7) : 0;
       t_steps[t] = hi > lo ? (hi - t_kstart[t] + 7) / 8 : 0;
+      plan->items[t] = MelItem{t, t_kstart[t], t_steps[t], total};
       total += t_steps[t];
     }
-    const int chunk = 1 << 30;  // items are whole filter groups: the contraction warps own complete outputs
-    int n_items = 0, off = 0;
-    for (int t = 0; t < n_tiles; ++t) {
-      const int parts = 1;
-      for (int q = 0; q < 4; ++q) plan->tiles[t].part[q] = q < parts ? n_items + q : kMaxItems;
-      for (int q = 0; q < parts; ++q) {  // near-equal parts
-        const int b0 = (int)((long long)t_steps[t] * q / parts), b1 = (int)((long long)t_steps[t] * (q + 1) / parts);
-        plan->items[n_items++] = MelItem{t, t_kstart[t] + 8 * b0, b1 - b0, off + b0};
-      }
-      off += t_steps[t];
-    }
     plan->n_tiles = n_tiles;
-    plan->n_items = n_items;
+    plan->n_items = n_tiles;
     plan->total_steps = total;
-    plan->chunk = chunk;
-    // longest-processing-time-first assignment of items to the contraction warps
+    plan->pad = 0;
+    // longest-processing-time-first assignment of the groups to the contraction warps
     int load[kWarps];
     bool used[kMaxItems];
     for (int w = 0; w < kWarps; ++w) { load[w] = 0; plan->warp_cnt[w] = 0; }
-    constexpr int kTargets = 4;  // == kMelWarps
-    for (int i = 0; i < n_items; ++i) used[i] = false;
-    for (int k = 0; k < n_items; ++k) {
+    for (int i = 0; i < n_tiles; ++i) used[i] = false;
+    for (int k = 0; k < n_tiles; ++k) {
       int best = -1;
-      for (int i = 0; i < n_items; ++i)
-        if (!used[i] && (best < 0 || plan->items[i].nsteps > plan->items[best].nsteps)) best = i;
+      for (int i = 0; i < n_tiles; ++i)
+        if (!used[i] && (best < 0 || t_steps[i] > t_steps[best])) best = i;
       used[best] = true;
       int w = 0;
-      for (int q = 1; q < kTargets; ++q)
+      for (int q = 1; q < kMelWarps; ++q)
         if (load[q] < load[w] || (load[q] == load[w] && plan->warp_cnt[q] < plan->warp_cnt[w])) w = q;
-      if (plan->warp_cnt[w] >= kMaxItemsPerWarp) {  // cannot happen with kMaxItems <= 2 * kMaxItemsPerWarp
-        for (w = 0; plan->warp_cnt[w] >= kMaxItemsPerWarp; ++w) {}
-      }
       plan->warp_items[w][plan->warp_cnt[w]++] = best;
-      load[w] += plan->items[best].nsteps + 2;  // + epilogue cost
+      load[w] += t_steps[best] + 2;  // + epilogue cost
     }
   }
   __syncthreads();
@@ -693,6 +735,9 @@ __global__ void prepare_mma_kernel(const float* __restrict__ fb, const int2* __r
   }
 }
 
+static_assert(kMaxItemsPerWarp * kMelWarps >= kMaxItems,
+              "every filter group must find a place in a contraction warp's list");
+
 }  // namespace
 
 size_t pow2_workspace_extra(const b200a_frontend_desc* d) {
@@ -707,8 +752,9 @@ int pow2_prepare(const b200a_frontend_desc* d, void* ws, size_t ws_bytes, cudaSt
   const Pow2Extra e = pow2_layout(*d, l.total);
   if (ws_bytes < e.total) return B200A_EWORKSPACE;
   unsigned char* base = static_cast<unsigned char*>(ws);
-  prepare_tw2d_kernel<<<4, 256, 0, stream>>>(reinterpret_cast<float2*>(base + e.tw2d));
-  if (d->n_mels > 0 && mel_tiles(d->n_mels) <= 64) {
+  const int G = d->n_fft / 32;
+  prepare_tw2d_kernel<<<(32 * G + 255) / 256, 256, 0, stream>>>(reinterpret_cast<float2*>(base + e.tw2d), G);
+  if (d->n_mels > 0 && mel_tiles(d->n_mels) <= kMaxItems) {
     prepare_mma_kernel<<<1, 256, 0, stream>>>(reinterpret_cast<const float*>(base + l.fb),
                                               reinterpret_cast<const int2*>(base + l.bands), d->n_fft / 2 + 1, d->n_mels,
                                               mel_tiles(d->n_mels), reinterpret_cast<MelPlan*>(base + e.plan),
@@ -728,20 +774,21 @@ static int num_sms() {
   return cached;
 }
 
-// persistent: one resident CTA per SM, pairs dealt round-robin (every CTA gets the same count +-1)
+// persistent: one resident CTA per SM, units dealt round-robin (every CTA gets the same count +-1)
 static int64_t persistent_grid(const Pow2Params& p) {
   const int sms = num_sms();
   if (sms < 0) return -1;
-  const int64_t iters = (p.total_pairs + kWarps - 1) / kWarps;
+  const int64_t iters = (p.total_units + kWarps - 1) / kWarps;
   const int64_t grid = iters < sms ? iters : sms;
   return grid < 1 ? 1 : grid;
 }
 
-template <int POWER_MODE, int HG>
+template <int POWER_MODE, int G, int HG>
 static int launch_power(const Pow2Params& p, cudaStream_t stream) {
-  const size_t smem = sizeof(float2) * (32 * 32 + kWarps * kTileFloat2) + sizeof(float) * kWarps * kStageFloats +
+  using Ge = Geo<G>;
+  const size_t smem = sizeof(float2) * (32 * 32 + kWarps * Ge::kTileF2) + sizeof(float) * kWarps * Ge::kStageFloats +
                       sizeof(uint64_t) * kWarps;
-  auto kern = stft1024_power_kernel<POWER_MODE, HG>;
+  auto kern = stft_pow2_power_kernel<POWER_MODE, G, HG>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return B200A_ECUDA;
   const int64_t grid = persistent_grid(p);
@@ -750,14 +797,16 @@ static int launch_power(const Pow2Params& p, cudaStream_t stream) {
   return launch_status();
 }
 
-template <int POWER_MODE, int HG>
+template <int POWER_MODE, int G, int HG>
 static int launch_mel(const Pow2Params& p, cudaStream_t stream) {
+  using Ge = Geo<G>;
   static_assert(sizeof(MelPlan) % 16 == 0, "fragment array must stay 16-byte aligned");
-  const size_t smem = sizeof(float2) * (32 * 32 + kWarps * kTileFloat2) + sizeof(float) * 2 * kSlots * kPowPitch +
-                      sizeof(int64_t) * 4 * kSlots + sizeof(uint64_t) * (kWarps + 4) + sizeof(MelPlan) +
+  static_assert(Ge::kSlots <= kMaxSlots, "slot tables");
+  const size_t smem = sizeof(float2) * (32 * 32 + kWarps * Ge::kTileF2) + sizeof(float) * 2 * Ge::kSlots * Ge::kPitch +
+                      sizeof(int64_t) * 4 * Ge::kSlots + sizeof(uint64_t) * (kWarps + 4) + sizeof(MelPlan) +
                       sizeof(float4) * 32 * kFragSmemSteps;
   if (smem > 227 * 1024) return B200A_EUNSUPPORTED;
-  auto kern = stft1024_mel_kernel<POWER_MODE, HG>;
+  auto kern = stft_pow2_mel_kernel<POWER_MODE, G, HG>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return B200A_ECUDA;
   const int64_t grid = persistent_grid(p);
@@ -766,28 +815,39 @@ static int launch_mel(const Pow2Params& p, cudaStream_t stream) {
   return launch_status();
 }
 
+template <int POWER_MODE, int G>
+static int launch_g(const Pow2Params& p, bool mel, cudaStream_t stream) {
+  if constexpr (G == 32) {
+    if (p.bulk_ok && p.hop == 256)  // frame b = frame a shifted by 8 lane-rows: shared register loads
+      return mel ? launch_mel<POWER_MODE, 32, 8>(p, stream) : launch_power<POWER_MODE, 32, 8>(p, stream);
+  }
+  return mel ? launch_mel<POWER_MODE, G, -1>(p, stream) : launch_power<POWER_MODE, G, -1>(p, stream);
+}
+
 template <int POWER_MODE>
-static int launch_hg(const Pow2Params& p, bool mel, cudaStream_t stream) {
-  const bool aligned_b = p.bulk_ok && p.hop == 256;
-  if (mel) return aligned_b ? launch_mel<POWER_MODE, 8>(p, stream) : launch_mel<POWER_MODE, -1>(p, stream);
-  return aligned_b ? launch_power<POWER_MODE, 8>(p, stream) : launch_power<POWER_MODE, -1>(p, stream);
+static int launch_any(Pow2Params& p, int n_fft, bool mel, cudaStream_t stream) {
+  if (n_fft == 1024) return launch_g<POWER_MODE, 32>(p, mel, stream);
+  if (n_fft == 512) return launch_g<POWER_MODE, 16>(p, mel, stream);
+  return launch_g<POWER_MODE, 8>(p, mel, stream);
 }
 
 int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, const float* wave, int64_t rows,
                       int64_t length, int64_t row_stride, int64_t frames, float* out, float* group_max,
                       int64_t rows_per_group, cudaStream_t stream) {
   if (!pow2_applicable(*d) || stage == B200A_STAGE_COMPLEX) return B200A_EUNSUPPORTED;
-  if (stage >= B200A_STAGE_MEL && mel_tiles(d->n_mels) > 64) return B200A_EUNSUPPORTED;  // > 512 filters: generic path
+  if (stage >= B200A_STAGE_MEL && mel_tiles(d->n_mels) > kMaxItems) return B200A_EUNSUPPORTED;  // > 512 filters
   const WsLayout l = ws_layout(*d);
   const Pow2Extra e = pow2_layout(*d, l.total);
   const unsigned char* base = static_cast<const unsigned char*>(ws);
+  const int G = d->n_fft / 32;
+  const int frames_per_unit = 2 * (32 / G);
   Pow2Params p{};
   p.wave = wave;
   p.length = length;
   p.row_stride = row_stride;
   p.frames = frames;
-  p.pairs_per_row = (frames + 1) / 2;
-  p.total_pairs = rows * p.pairs_per_row;
+  p.units_per_row = (frames + frames_per_unit - 1) / frames_per_unit;
+  p.total_units = rows * p.units_per_row;
   p.out = out;
   p.group_max = group_max;
   p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
@@ -807,12 +867,15 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
   p.db_mult = d->db_multiplier;
   p.db_amin = d->db_amin;
   p.db_offset = d->db_offset;
-  // bulk staging needs 16-byte aligned sources and sizes: every pair starts at 2*pr*hop - half - pad
-  const int half = d->center ? kN / 2 : 0;
-  p.bulk_ok = d->hop <= kMaxHopBulk && d->hop % 4 == 0 && (half + d->pad) % 4 == 0 && row_stride % 4 == 0 &&
-              (reinterpret_cast<uintptr_t>(wave) & 15) == 0;
+  // bulk staging needs 16-byte aligned sources and sizes (every unit starts at a multiple of
+  // frames_per_unit*hop, minus half + pad) and the unit's span must fit the staging buffer
+  const int half = d->center ? d->n_fft / 2 : 0;
+  const int stage_floats = 2 * (32 / G) * (32 * (G + 1) + (G == 8 ? 8 : 0));
+  p.bulk_ok = d->hop % 4 == 0 && (half + d->pad) % 4 == 0 && row_stride % 4 == 0 &&
+              (reinterpret_cast<uintptr_t>(wave) & 15) == 0 &&
+              d->n_fft + (frames_per_unit - 1) * (int64_t)d->hop <= stage_floats;
   const bool mel = stage >= B200A_STAGE_MEL;
-  return d->power == 2.f ? launch_hg<2>(p, mel, stream) : launch_hg<0>(p, mel, stream);
+  return d->power == 2.f ? launch_any<2>(p, d->n_fft, mel, stream) : launch_any<0>(p, d->n_fft, mel, stream);
 }
 
 }  // namespace b200a
