@@ -1,4 +1,4 @@
-// Register-FFT fast path of the fused front end (n_fft = 256 / 512 / 1024, one-sided, real output stages).
+// Register-FFT fast path of the fused front end (n_fft = 256 / 512 / 1024 / 2048, one-sided, real output stages).
 //
 // A group of G = n_fft/32 lanes transforms one PAIR of consecutive frames (a, b); a warp holds 32/G
 // such groups (1, 2 or 4 pairs = 2, 4 or 8 consecutive frames of one utterance = one "unit"):
@@ -78,7 +78,7 @@ struct MelPlan {  // built on the device by prepare_mma_kernel
 };
 
 struct Pow2Extra {  // tables appended to the generic workspace
-  size_t tw2d, plan, frags, total;
+  size_t tw2d, tw_eo, plan, frags, total;
 };
 
 inline int mel_tiles(int n_mels) { return (n_mels + 7) / 8; }
@@ -90,6 +90,8 @@ inline Pow2Extra pow2_layout(const b200a_frontend_desc& d, size_t base) {
   size_t off = base;
   e.tw2d = off;
   off = align_up(off + sizeof(float2) * 32 * 32, 256);
+  e.tw_eo = off;
+  off = align_up(off + sizeof(float2) * 17 * 32, 256);
   e.plan = off;
   off = align_up(off + sizeof(MelPlan), 256);
   e.frags = off;  // worst case: every tile spans every bin
@@ -99,7 +101,7 @@ inline Pow2Extra pow2_layout(const b200a_frontend_desc& d, size_t base) {
 }
 
 bool pow2_applicable(const b200a_frontend_desc& d) {
-  return (d.n_fft == 1024 || d.n_fft == 512 || d.n_fft == 256) && d.onesided != 0;
+  return (d.n_fft == 2048 || d.n_fft == 1024 || d.n_fft == 512 || d.n_fft == 256) && d.onesided != 0;
 }
 
 // ---- compile-time helpers -----------------------------------------------------------------
@@ -482,6 +484,74 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stft_pow2_power_kernel(const P
   }
 }
 
+// One contraction warp's share of a 16-frame power tile: D[16 x 8] = P[16 x bins] * F[bins x 8] for each of its
+// filter groups on the tensor pipe, (dB / log), store.  pw: the tile's 16 power rows (pitch PITCH);
+// slot / grp: output offset (or -1) and top_db group of each of the 16 rows.
+template <int PITCH>
+__device__ __forceinline__ void contract_tile(const Pow2Params& p, const MelPlan* s_plan, const float4* s_frags,
+                                              bool frags_in_smem, int mw, int lane, const float* pw,
+                                              const int64_t* slot, const int64_t* grp, GroupMax& gmax) {
+  const int r = lane >> 2, c = lane & 3;
+  const int cnt = s_plan->warp_cnt[mw];
+  const int width = p.n_mels;
+  const int64_t o_lo = slot[r], o_hi = slot[r + 8];
+  const int64_t g_lo = grp[r], g_hi = grp[r + 8];
+  for (int ii = 0; ii < cnt; ++ii) {
+    const MelItem mi = s_plan->items[s_plan->warp_items[mw][ii]];
+    const float* a_lo_row = pw + (size_t)r * PITCH + mi.kstart + c;
+    const float* a_hi_row = a_lo_row + 8 * PITCH;
+    // three independent accumulator chains (hi*hi, lo*hi, hi*lo), summed in a fixed order
+    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+    auto contract = [&](auto in_smem) {
+      const float4* fr = (decltype(in_smem)::value ? s_frags : p.frags) + (size_t)mi.frag_off * 32 + lane;
+#pragma unroll 4
+      for (int s = 0; s < mi.nsteps; ++s) {
+        float4 bf;
+        if constexpr (decltype(in_smem)::value) bf = fr[(size_t)s * 32];
+        else bf = __ldg(fr + (size_t)s * 32);
+        const float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split_tf32(av[q], hi[q], lo[q]);
+        mma_tf32(d0, hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
+        mma_tf32(d1, lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
+        mma_tf32(d2, hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
+      }
+    };
+    if (frags_in_smem) contract(std::true_type{});
+    else contract(std::false_type{});
+    float d[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) d[q] = d0[q] + (d1[q] + d2[q]);
+    const int n0 = 8 * mi.tile + 2 * c;
+    const bool n0_ok = n0 < p.n_mels, n1_ok = n0 + 1 < p.n_mels;
+    if (p.stage == B200A_STAGE_FEAT) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        d[q] = p.log_mels ? logf(d[q] + 1e-6f) : p.db_mult * log10f(fmaxf(d[q], p.db_amin)) - p.db_offset;
+      const float m_lo = fmaxf(n0_ok ? d[0] : -CUDART_INF_F, n1_ok ? d[1] : -CUDART_INF_F);
+      const float m_hi = fmaxf(n0_ok ? d[2] : -CUDART_INF_F, n1_ok ? d[3] : -CUDART_INF_F);
+      gmax.add(g_lo, m_lo, o_lo >= 0);
+      gmax.add(g_hi, m_hi, o_hi >= 0);
+    }
+    const bool vec = n1_ok && (width & 1) == 0;  // 8-byte aligned pair
+    if (o_lo >= 0) {
+      if (vec) *reinterpret_cast<float2*>(p.out + o_lo + n0) = make_float2(d[0], d[1]);
+      else {
+        if (n0_ok) p.out[o_lo + n0] = d[0];
+        if (n1_ok) p.out[o_lo + n0 + 1] = d[1];
+      }
+    }
+    if (o_hi >= 0) {
+      if (vec) *reinterpret_cast<float2*>(p.out + o_hi + n0) = make_float2(d[2], d[3]);
+      else {
+        if (n0_ok) p.out[o_hi + n0] = d[2];
+        if (n1_ok) p.out[o_hi + n0 + 1] = d[3];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Mel / MFCC-feature kernel, warp specialised: warps 0-7 transform (one unit each per iteration)
 // and publish power rows into a double-buffered shared tile; warps 8-11 contract each finished tile
@@ -594,76 +664,302 @@ __global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft_pow2_mel_ke
     reg_dealloc<kMelRegs>();
     const int mw = warp - kWarps;
     GroupMax gmax{p.stage == B200A_STAGE_FEAT ? p.group_max : nullptr, -1, -CUDART_INF_F};
-    const int r = lane >> 2, c = lane & 3;
-    const int cnt = s_plan->warp_cnt[mw];
     int it = 0;
     for (int64_t base = u0; base < p.total_units; base += stride, ++it) {
       const int b = it & 1;
       mbar_wait(s_full + b, (it >> 1) & 1);
 #pragma unroll 1
-      for (int mt = 0; mt < kSlots / 16; ++mt) {  // 16-frame MMA tiles of this iteration
-        const float* pw = s_pow + (size_t)(b * kSlots + 16 * mt) * kPitch;
-        const int64_t o_lo = s_slot[b * kSlots + 16 * mt + r], o_hi = s_slot[b * kSlots + 16 * mt + r + 8];
-        const int64_t g_lo = s_grp[b * kSlots + 16 * mt + r], g_hi = s_grp[b * kSlots + 16 * mt + r + 8];
-        for (int ii = 0; ii < cnt; ++ii) {
-          const MelItem mi = s_plan->items[s_plan->warp_items[mw][ii]];
-          const float* a_lo_row = pw + (size_t)r * kPitch + mi.kstart + c;
-          const float* a_hi_row = a_lo_row + 8 * kPitch;
-          // three independent accumulator chains (hi*hi, lo*hi, hi*lo), summed in a fixed order
-          float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
-          auto contract = [&](auto in_smem) {
-            const float4* fr = (decltype(in_smem)::value ? s_frags : p.frags) + (size_t)mi.frag_off * 32 + lane;
-#pragma unroll 4
-            for (int s = 0; s < mi.nsteps; ++s) {
-              float4 bf;
-              if constexpr (decltype(in_smem)::value) bf = fr[(size_t)s * 32];
-              else bf = __ldg(fr + (size_t)s * 32);
-              const float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) split_tf32(av[q], hi[q], lo[q]);
-              mma_tf32(d0, hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
-              mma_tf32(d1, lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
-              mma_tf32(d2, hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
-            }
-          };
-          if (frags_in_smem) contract(std::true_type{});
-          else contract(std::false_type{});
-          float d[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) d[q] = d0[q] + (d1[q] + d2[q]);
-          const int n0 = 8 * mi.tile + 2 * c;
-          const bool n0_ok = n0 < p.n_mels, n1_ok = n0 + 1 < p.n_mels;
-          if (p.stage == B200A_STAGE_FEAT) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              d[q] = p.log_mels ? logf(d[q] + 1e-6f) : p.db_mult * log10f(fmaxf(d[q], p.db_amin)) - p.db_offset;
-            const float m_lo = fmaxf(n0_ok ? d[0] : -CUDART_INF_F, n1_ok ? d[1] : -CUDART_INF_F);
-            const float m_hi = fmaxf(n0_ok ? d[2] : -CUDART_INF_F, n1_ok ? d[3] : -CUDART_INF_F);
-            gmax.add(g_lo, m_lo, o_lo >= 0);
-            gmax.add(g_hi, m_hi, o_hi >= 0);
-          }
-          const bool vec = n1_ok && (width & 1) == 0;  // 8-byte aligned pair
-          if (o_lo >= 0) {
-            if (vec) *reinterpret_cast<float2*>(p.out + o_lo + n0) = make_float2(d[0], d[1]);
-            else {
-              if (n0_ok) p.out[o_lo + n0] = d[0];
-              if (n1_ok) p.out[o_lo + n0 + 1] = d[1];
-            }
-          }
-          if (o_hi >= 0) {
-            if (vec) *reinterpret_cast<float2*>(p.out + o_hi + n0) = make_float2(d[2], d[3]);
-            else {
-              if (n0_ok) p.out[o_hi + n0] = d[2];
-              if (n1_ok) p.out[o_hi + n0 + 1] = d[3];
-            }
-          }
-        }
-      }
+      for (int mt = 0; mt < kSlots / 16; ++mt)  // 16-frame MMA tiles of this iteration
+        contract_tile<kPitch>(p, s_plan, s_frags, frags_in_smem, mw, lane, s_pow + (size_t)(b * kSlots + 16 * mt) * kPitch,
+                              s_slot + b * kSlots + 16 * mt, s_grp + b * kSlots + 16 * mt, gmax);
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty + b);
     }
     gmax.flush();
+  }
+}
+
+// ================================================================================================
+// n_fft = 2048: one real frame per 1024-point complex FFT ("even/odd packing").
+//   z[m] = w[2m] x[2m] + i w[2m+1] x[2m+1],  Z = FFT_1024(z);  with E = (Z[k] + conj Z[1024-k]) / 2 and
+//   O = (Z[k] - conj Z[1024-k]) / 2i:   X[k] = E + W_2048^k O,   X[1024-k] = conj(E - W_2048^k O),
+// so each lane turns its 16 (Z[k], Z[1024-k]) pairs into 32 power bins.  The same 32 x 32 register FFT,
+// tile transposes, bulk staging and tensor-pipe contraction as above; a warp handles 2 frames per iteration
+// one after the other, and the (16 x 1025) power tile is single buffered.
+// ================================================================================================
+constexpr int kEoN = 2048, kEoBins = 1025, kEoPitch = 1060, kEoSlots = 16;
+constexpr int kEoFragSteps = 136;  // fragments kept in shared memory when the plan has at most this many steps
+
+__device__ __forceinline__ bool eo_frame_bulk_ok(const Pow2Params& p, int half, int64_t t) {
+  const int64_t sa = t * p.hop - half - p.pad;
+  return p.bulk_ok && t < p.frames && sa >= 0 && sa + kEoN <= p.length;
+}
+
+// One warp, one frame of 2048 samples.  On return lane l holds bins l + 32 k1 in plo[k1], bins
+// 1024 - l - 32 k1 in phi[k1] (k1 < 16), and lane 0 bin 512 in pmid.
+template <int POWER_MODE>
+__device__ __forceinline__ void transform_frame_eo(const Pow2Params& p, const float2* s_win, const float2* s_tw,
+                                                   const float2* s_tw2, float2* tile, uint64_t* bar, uint32_t& parity,
+                                                   bool& staged, int64_t row, int64_t t, bool next_ok, int64_t next_row,
+                                                   int64_t next_t, int half, int lane, float (&plo)[16],
+                                                   float (&phi)[16], float& pmid) {
+  const float* __restrict__ x = p.wave + row * p.row_stride;
+  const int64_t sa = t * p.hop - half - p.pad;
+  float* stage = reinterpret_cast<float*>(tile);
+  float2 a[32];
+  if (staged) {
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    const float2* st2 = reinterpret_cast<const float2*>(stage);
+    static_for<32>([&](auto ji) {
+      constexpr int j = decltype(ji)::value;
+      const float2 v = st2[lane + 32 * j], w = s_win[lane + 32 * j];
+      a[brev5(j)] = make_float2(v.x * w.x, v.y * w.y);
+    });
+    __syncwarp();
+  } else if (sa >= 0 && sa + kEoN <= p.length) {
+    static_for<32>([&](auto ji) {
+      constexpr int j = decltype(ji)::value;
+      const float2 w = s_win[lane + 32 * j];
+      const float ve = __ldg(x + sa + 2 * (lane + 32 * j)), vo = __ldg(x + sa + 2 * (lane + 32 * j) + 1);
+      a[brev5(j)] = make_float2(ve * w.x, vo * w.y);
+    });
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) {
+      const int m = lane + 32 * j;
+      const int64_t ie = source_index(t * p.hop + 2 * m, p.length, p.pad, half, p.pad_mode);
+      const int64_t io = source_index(t * p.hop + 2 * m + 1, p.length, p.pad, half, p.pad_mode);
+      tile[m] = make_float2(ie >= 0 ? __ldg(x + ie) : 0.f, io >= 0 ? __ldg(x + io) : 0.f);
+    }
+    __syncwarp();
+    static_for<32>([&](auto ji) {
+      constexpr int j = decltype(ji)::value;
+      const float2 v = tile[lane + 32 * j], w = s_win[lane + 32 * j];
+      a[brev5(j)] = make_float2(v.x * w.x, v.y * w.y);
+    });
+    __syncwarp();
+  }
+
+  fft_regs<32, 0>(a);
+  tile[lane] = a[0];
+  static_for<31>([&](auto ki) {
+    constexpr int k2 = decltype(ki)::value + 1;
+    const float2 w = s_tw[k2 * 32 + lane];
+    const float2 v = a[k2];
+    tile[k2 * 33 + lane] = make_float2(fmaf(v.x, w.x, -v.y * w.y), fmaf(v.x, w.y, v.y * w.x));
+  });
+  __syncwarp();
+  static_for<32>([&](auto gi) {
+    constexpr int g = decltype(gi)::value;
+    a[brev5(g)] = tile[lane * 33 + g];
+  });
+  __syncwarp();
+  staged = next_ok && eo_frame_bulk_ok(p, half, next_t);
+  if (staged && lane == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const float* src = p.wave + next_row * p.row_stride + (next_t * p.hop - half - p.pad);
+    mbar_expect_tx(bar, kEoN * 4u);
+    bulk_g2s(stage, src, kEoN * 4u, bar);
+  }
+  fft_regs<32, 0>(a);  // a[k1] = Z[lane + 32 k1]
+
+  const int src_lane = (32 - lane) & 31;
+  static_for<16>([&](auto ki) {
+    constexpr int k1 = decltype(ki)::value;
+    float mr = __shfl_sync(0xffffffffu, a[31 - k1].x, src_lane);
+    float mi = __shfl_sync(0xffffffffu, a[31 - k1].y, src_lane);
+    if (lane == 0) {
+      mr = a[(32 - k1) & 31].x;
+      mi = a[(32 - k1) & 31].y;
+    }
+    const float zr = a[k1].x, zi = a[k1].y;
+    const float er = zr + mr, ei = zi - mi;   // E (x 2, the 1/2 rides on the window)
+    const float orr = zi + mi, oi = mr - zr;  // O
+    const float2 w = s_tw2[k1 * 32 + lane];   // W_2048^(lane + 32 k1)
+    const float tr = fmaf(orr, w.x, -oi * w.y), ti = fmaf(orr, w.y, oi * w.x);
+    plo[k1] = pow_of<POWER_MODE>(er + tr, ei + ti, p.power);
+    phi[k1] = pow_of<POWER_MODE>(er - tr, ei - ti, p.power);
+  });
+  // bin 512 = lane 0, slot 16: E = 2 Re Z, O = 2 Im Z, W^512 = -i  ->  X = E - i O
+  pmid = pow_of<POWER_MODE>(2.f * a[16].x, -2.f * a[16].y, p.power);
+}
+
+__device__ __forceinline__ void eo_store_row(float* row, int lane, const float (&plo)[16], const float (&phi)[16],
+                                             float pmid) {
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) {
+    row[lane + 32 * k1] = plo[k1];
+    row[1024 - lane - 32 * k1] = phi[k1];
+  }
+  if (lane == 0) row[512] = pmid;
+}
+
+__device__ __forceinline__ void eo_load_tables(const Pow2Params& p, const float2* tw_eo, float2* s_win, float2* s_tw,
+                                               float2* s_tw2, int tid, int nthreads) {
+  const float hs = 0.5f * p.hdr->scale;
+  for (int i = tid; i < 1024; i += nthreads) {
+    s_tw[i] = p.tw2d[i];
+    s_win[i] = make_float2(p.window[2 * i] * hs, p.window[2 * i + 1] * hs);
+  }
+  for (int i = tid; i < 17 * 32; i += nthreads) s_tw2[i] = tw_eo[i];
+}
+
+struct EoNext {  // the frame that follows (row, t) in this warp's walk
+  bool ok;
+  int64_t row, t;
+};
+__device__ __forceinline__ EoNext eo_next_frame(const Pow2Params& p, const UnitCursor& cur, int f) {
+  if (f == 0) return EoNext{true, cur.row, 2 * cur.ub + 1};
+  return EoNext{cur.u + cur.stride < p.total_units, cur.nrow, 2 * cur.nub};
+}
+
+template <int POWER_MODE>
+__global__ void __launch_bounds__(kWarps * 32, 1) stft2048_power_kernel(const Pow2Params p, const float2* tw_eo) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);   // [32][32]
+  float2* s_win = s_tw + 1024;                          // [1024] (w[2m], w[2m+1]) x scale
+  float2* s_tw2 = s_win + 1024;                         // [17][32] W_2048^(l + 32 k1)
+  float2* s_tile_all = s_tw2 + 17 * 32;                 // [kWarps][32 * 33]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile_all + kWarps * 32 * 33);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  eo_load_tables(p, tw_eo, s_win, s_tw, s_tw2, tid, blockDim.x);
+  if (tid < kWarps) mbar_init(s_bar + tid, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  float2* tile = s_tile_all + warp * 32 * 33;
+  uint64_t* bar = s_bar + warp;
+  const int half = p.center ? kEoN / 2 : 0;
+  uint32_t parity = 0;
+  bool staged = false;
+  UnitCursor cur;
+  cur.init((int64_t)blockIdx.x * kWarps + warp, (int64_t)gridDim.x * kWarps, p.units_per_row);
+  if (cur.u < p.total_units && eo_frame_bulk_ok(p, half, 2 * cur.ub)) {
+    if (lane == 0) {
+      mbar_expect_tx(bar, kEoN * 4u);
+      bulk_g2s(tile, p.wave + cur.row * p.row_stride + (2 * cur.ub * p.hop - half - p.pad), kEoN * 4u, bar);
+    }
+    staged = true;
+  }
+  for (; cur.u < p.total_units; cur.advance()) {
+#pragma unroll 1
+    for (int f = 0; f < 2; ++f) {
+      const int64_t t = 2 * cur.ub + f;
+      if (t >= p.frames) { staged = false; break; }  // (never staged: eo_frame_bulk_ok checks t < frames)
+      const EoNext nx = eo_next_frame(p, cur, f);
+      float plo[16], phi[16], pmid;
+      transform_frame_eo<POWER_MODE>(p, s_win, s_tw, s_tw2, tile, bar, parity, staged, cur.row, t, nx.ok, nx.row, nx.t,
+                                     half, lane, plo, phi, pmid);
+      eo_store_row(p.out + (cur.row * p.frames + t) * kEoBins, lane, plo, phi, pmid);
+    }
+  }
+}
+
+template <int POWER_MODE>
+__global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft2048_mel_kernel(const Pow2Params p,
+                                                                                     const float2* tw_eo) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);
+  float2* s_win = s_tw + 1024;
+  float2* s_tw2 = s_win + 1024;
+  float2* s_tile_all = s_tw2 + 17 * 32;
+  float* s_pow = reinterpret_cast<float*>(s_tile_all + kWarps * 32 * 33);  // [kEoSlots][kEoPitch]
+  int64_t* s_slot = reinterpret_cast<int64_t*>(s_pow + kEoSlots * kEoPitch);
+  int64_t* s_grp = s_slot + kEoSlots;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + kEoSlots);  // [kWarps] staging, full, empty
+  uint64_t* s_full = s_bar + kWarps;
+  uint64_t* s_empty = s_full + 1;
+  MelPlan* s_plan = reinterpret_cast<MelPlan*>(s_empty + 1);
+  float4* s_frags = reinterpret_cast<float4*>(s_plan + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  eo_load_tables(p, tw_eo, s_win, s_tw, s_tw2, tid, blockDim.x);
+  {
+    const int* src = reinterpret_cast<const int*>(p.plan);
+    int* dst = reinterpret_cast<int*>(s_plan);
+    for (int i = tid; i < (int)(sizeof(MelPlan) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+  }
+  const int total_steps = p.plan->total_steps;
+  const bool frags_in_smem = total_steps <= kEoFragSteps;
+  if (frags_in_smem)
+    for (int i = tid; i < total_steps * 32; i += blockDim.x) s_frags[i] = p.frags[i];
+  for (int i = tid; i < kEoSlots * (kEoPitch - kEoBins); i += blockDim.x) {
+    const int r = i / (kEoPitch - kEoBins), c = i - r * (kEoPitch - kEoBins);
+    s_pow[r * kEoPitch + kEoBins + c] = 0.f;
+  }
+  if (tid < kWarps) mbar_init(s_bar + tid, 1);
+  if (tid == 0) {
+    mbar_init(s_full, kWarps);
+    mbar_init(s_empty, kMelWarps);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const int64_t stride = (int64_t)gridDim.x * kWarps;
+  const int64_t u0 = (int64_t)blockIdx.x * kWarps;
+  if (warp < kWarps) {
+    reg_alloc<kFftRegs>();
+    float2* tile = s_tile_all + warp * 32 * 33;
+    uint64_t* bar = s_bar + warp;
+    const int half = p.center ? kEoN / 2 : 0;
+    uint32_t parity = 0;
+    bool staged = false;
+    UnitCursor cur;
+    cur.init(u0 + warp, stride, p.units_per_row);
+    if (cur.u < p.total_units && eo_frame_bulk_ok(p, half, 2 * cur.ub)) {
+      if (lane == 0) {
+        mbar_expect_tx(bar, kEoN * 4u);
+        bulk_g2s(tile, p.wave + cur.row * p.row_stride + (2 * cur.ub * p.hop - half - p.pad), kEoN * 4u, bar);
+      }
+      staged = true;
+    }
+    int it = 0;
+    for (int64_t base = u0; base < p.total_units; base += stride, ++it, cur.advance()) {
+      const bool valid = cur.u < p.total_units;
+#pragma unroll 1
+      for (int f = 0; f < 2; ++f) {
+        const int64_t t = 2 * cur.ub + f;
+        const bool live = valid && t < p.frames;
+        float plo[16], phi[16], pmid = 0.f;
+        if (live) {
+          const EoNext nx = eo_next_frame(p, cur, f);
+          transform_frame_eo<POWER_MODE>(p, s_win, s_tw, s_tw2, tile, bar, parity, staged, cur.row, t, nx.ok, nx.row,
+                                         nx.t, half, lane, plo, phi, pmid);
+        } else {
+          staged = false;
+        }
+        if (f == 0 && it >= 1) mbar_wait(s_empty, (it - 1) & 1);  // the contraction warps have drained the tile
+        if (live) eo_store_row(s_pow + (size_t)(2 * warp + f) * kEoPitch, lane, plo, phi, pmid);
+        if (lane == 0) {
+          s_slot[2 * warp + f] = live ? (cur.row * p.frames + t) * (int64_t)p.n_mels : -1;
+          s_grp[2 * warp + f] = cur.row / p.rows_per_group;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_full);
+    }
+  } else {
+    reg_dealloc<kMelRegs>();
+    const int mw = warp - kWarps;
+    GroupMax gmax{p.stage == B200A_STAGE_FEAT ? p.group_max : nullptr, -1, -CUDART_INF_F};
+    int it = 0;
+    for (int64_t base = u0; base < p.total_units; base += stride, ++it) {
+      mbar_wait(s_full, it & 1);
+      contract_tile<kEoPitch>(p, s_plan, s_frags, frags_in_smem, mw, lane, s_pow, s_slot, s_grp, gmax);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+    }
+    gmax.flush();
+  }
+}
+
+__global__ void prepare_tw_eo_kernel(float2* tw_eo) {  // [17][32]: W_2048^(l + 32 k1)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 17 * 32) {
+    const int k1 = i >> 5, l = i & 31;
+    double s, c;
+    sincospi(-2.0 * (double)(l + 32 * k1) / 2048.0, &s, &c);
+    tw_eo[i] = make_float2((float)c, (float)s);
   }
 }
 
@@ -752,8 +1048,9 @@ int pow2_prepare(const b200a_frontend_desc* d, void* ws, size_t ws_bytes, cudaSt
   const Pow2Extra e = pow2_layout(*d, l.total);
   if (ws_bytes < e.total) return B200A_EWORKSPACE;
   unsigned char* base = static_cast<unsigned char*>(ws);
-  const int G = d->n_fft / 32;
+  const int G = d->n_fft == 2048 ? 32 : d->n_fft / 32;  // 2048 runs on the 1024-point complex core
   prepare_tw2d_kernel<<<(32 * G + 255) / 256, 256, 0, stream>>>(reinterpret_cast<float2*>(base + e.tw2d), G);
+  if (d->n_fft == 2048) prepare_tw_eo_kernel<<<3, 256, 0, stream>>>(reinterpret_cast<float2*>(base + e.tw_eo));
   if (d->n_mels > 0 && mel_tiles(d->n_mels) <= kMaxItems) {
     prepare_mma_kernel<<<1, 256, 0, stream>>>(reinterpret_cast<const float*>(base + l.fb),
                                               reinterpret_cast<const int2*>(base + l.bands), d->n_fft / 2 + 1, d->n_mels,
@@ -831,6 +1128,28 @@ static int launch_any(Pow2Params& p, int n_fft, bool mel, cudaStream_t stream) {
   return launch_g<POWER_MODE, 8>(p, mel, stream);
 }
 
+template <int POWER_MODE>
+static int launch_eo(const Pow2Params& p, const float2* tw_eo, bool mel, cudaStream_t stream) {
+  const int64_t grid = persistent_grid(p);
+  if (grid < 0) return B200A_ECUDA;
+  const size_t tables = sizeof(float2) * (1024 + 1024 + 17 * 32 + kWarps * 32 * 33);
+  if (!mel) {
+    auto kern = stft2048_power_kernel<POWER_MODE>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return B200A_ECUDA;
+    kern<<<(unsigned)grid, kWarps * 32, tables + sizeof(uint64_t) * kWarps, stream>>>(p, tw_eo);
+    return launch_status();
+  }
+  const size_t smem = tables + sizeof(float) * kEoSlots * kEoPitch + sizeof(int64_t) * 2 * kEoSlots +
+                      sizeof(uint64_t) * (kWarps + 2) + sizeof(MelPlan) + sizeof(float4) * 32 * kEoFragSteps;
+  if (smem > 227 * 1024) return B200A_EUNSUPPORTED;
+  auto kern = stft2048_mel_kernel<POWER_MODE>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return B200A_ECUDA;
+  kern<<<(unsigned)grid, (kWarps + kMelWarps) * 32, smem, stream>>>(p, tw_eo);
+  return launch_status();
+}
+
 int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, const float* wave, int64_t rows,
                       int64_t length, int64_t row_stride, int64_t frames, float* out, float* group_max,
                       int64_t rows_per_group, cudaStream_t stream) {
@@ -839,7 +1158,8 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
   const WsLayout l = ws_layout(*d);
   const Pow2Extra e = pow2_layout(*d, l.total);
   const unsigned char* base = static_cast<const unsigned char*>(ws);
-  const int G = d->n_fft / 32;
+  const bool eo = d->n_fft == 2048;
+  const int G = eo ? 32 : d->n_fft / 32;
   const int frames_per_unit = 2 * (32 / G);
   Pow2Params p{};
   p.wave = wave;
@@ -875,6 +1195,12 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
               (reinterpret_cast<uintptr_t>(wave) & 15) == 0 &&
               d->n_fft + (frames_per_unit - 1) * (int64_t)d->hop <= stage_floats;
   const bool mel = stage >= B200A_STAGE_MEL;
+  if (eo) {
+    p.bulk_ok = d->hop % 4 == 0 && (half + d->pad) % 4 == 0 && row_stride % 4 == 0 &&
+                (reinterpret_cast<uintptr_t>(wave) & 15) == 0;
+    const float2* tw_eo = reinterpret_cast<const float2*>(base + e.tw_eo);
+    return d->power == 2.f ? launch_eo<2>(p, tw_eo, mel, stream) : launch_eo<0>(p, tw_eo, mel, stream);
+  }
   return d->power == 2.f ? launch_any<2>(p, d->n_fft, mel, stream) : launch_any<0>(p, d->n_fft, mel, stream);
 }
 
