@@ -280,6 +280,71 @@ mfcc_finish_kernel(const float* __restrict__ feat, int64_t total_rows, int64_t f
   }
 }
 
+// Register-tiled variant (n_mfcc <= 64, the usual case): a CTA walks tiles of 128 feature rows; each
+// thread owns 4 rows x CPT coefficient columns (columns strided by 8 so that the DCT reads of a warp and
+// its output stores are contiguous), features are clamped while they are staged into a padded tile.
+constexpr int kFinRows = 128;
+
+template <int CPT>
+__global__ void __launch_bounds__(256)
+mfcc_finish_tiled_kernel(const float* __restrict__ feat, int64_t total_rows, int64_t frames, int n_mels, int n_mfcc,
+                         const float* __restrict__ dct, const float* __restrict__ group_max, int64_t rows_per_group,
+                         float top_db, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_dct = reinterpret_cast<float*>(smem_raw);  // [n_mels][8 * CPT], zero padded columns
+  const int dld = 8 * CPT;
+  const int ld = n_mels + 1;
+  float* s_feat = s_dct + (size_t)n_mels * dld;       // [kFinRows][n_mels + 1]
+  for (int i = threadIdx.x; i < n_mels * dld; i += blockDim.x) {
+    const int m = i / dld, c = i - m * dld;
+    s_dct[i] = c < n_mfcc ? dct[m * n_mfcc + c] : 0.f;
+  }
+  const bool clamp = group_max != nullptr && top_db >= 0.f;
+  const int rg = threadIdx.x >> 3, cg = threadIdx.x & 7;  // 32 row groups of 4 rows, 8 column groups
+  const int64_t n_tiles = (total_rows + kFinRows - 1) / kFinRows;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * kFinRows;
+    const int rows = (int)min((int64_t)kFinRows, total_rows - r0);
+    __syncthreads();  // the previous tile has been consumed (and s_dct is complete on the first pass)
+    for (int i = threadIdx.x; i < rows * n_mels; i += blockDim.x) {
+      const int r = i / n_mels, m = i - r * n_mels;
+      float v = feat[r0 * n_mels + i];
+      if (clamp) v = fmaxf(v, group_max[((r0 + r) / frames) / rows_per_group] - top_db);
+      s_feat[r * ld + m] = v;
+    }
+    __syncthreads();
+    float acc[4][CPT];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) acc[q][i] = 0.f;
+    const float* f0 = s_feat + (size_t)(4 * rg) * ld;
+#pragma unroll 4
+    for (int m = 0; m < n_mels; ++m) {
+      float dv[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) dv[i] = s_dct[m * dld + cg + 8 * i];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a = f0[q * ld + m];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) acc[q][i] = fmaf(a, dv[i], acc[q][i]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = 4 * rg + q;
+      if (r < rows) {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          const int c = cg + 8 * i;
+          if (c < n_mfcc) out[(r0 + r) * n_mfcc + c] = acc[q][i];
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -388,6 +453,20 @@ int mfcc_finish_impl(const b200a_frontend_desc* d, const void* ws, const float* 
   const float* dct = reinterpret_cast<const float*>(static_cast<const unsigned char*>(ws) + l.dct);
   const int64_t total = rows * frames;
   if (total == 0) return B200A_OK;
+  if (d->n_mfcc <= 64) {  // register-tiled persistent kernel
+    const int cpt = d->n_mfcc <= 40 ? 5 : 8;
+    const size_t tsmem = sizeof(float) * ((size_t)d->n_mels * 8 * cpt + (size_t)kFinRows * (d->n_mels + 1));
+    if (tsmem <= 200 * 1024) {
+      auto kern = cpt == 5 ? mfcc_finish_tiled_kernel<5> : mfcc_finish_tiled_kernel<8>;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return B200A_ECUDA;
+      const int64_t tiles = (total + kFinRows - 1) / kFinRows;
+      const int64_t grid = tiles < 148 * 4 ? tiles : 148 * 4;
+      kern<<<(unsigned)grid, 256, tsmem, stream>>>(feat, total, frames, d->n_mels, d->n_mfcc, dct, group_max,
+                                                   rows_per_group > 0 ? rows_per_group : 1, top_db, out);
+      return launch_status();
+    }
+  }
   const size_t smem = sizeof(float) * ((size_t)d->n_mels * d->n_mfcc + (size_t)kDctRowsPerBlock * (d->n_mels + 1));
   if (smem > 200 * 1024) return B200A_EUNSUPPORTED;
   if (cudaFuncSetAttribute(mfcc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)

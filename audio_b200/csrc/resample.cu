@@ -26,7 +26,7 @@ namespace b200a {
 
 namespace {
 
-constexpr int kRsWarps = 8;
+constexpr int kRsWarps = 16;
 constexpr int kRsFrames = 32;        // frames per CTA tile (two 16-row MMA tiles)
 constexpr int kRsMaxTiles = 128;     // groups of 8 phases  (new' <= 1024)
 constexpr int kRsSmemBudget = 224 * 1024;
