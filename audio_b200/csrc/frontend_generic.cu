@@ -295,6 +295,7 @@ mfcc_finish_tiled_kernel(const float* __restrict__ feat, int64_t total_rows, int
   const int dld = 8 * CPT;
   const int ld = n_mels + 1;
   float* s_feat = s_dct + (size_t)n_mels * dld;       // [kFinRows][n_mels + 1]
+  float* s_floor = s_feat + (size_t)kFinRows * ld;    // [kFinRows] clamp floor of each row
   for (int i = threadIdx.x; i < n_mels * dld; i += blockDim.x) {
     const int m = i / dld, c = i - m * dld;
     s_dct[i] = c < n_mfcc ? dct[m * n_mfcc + c] : 0.f;
@@ -306,11 +307,28 @@ mfcc_finish_tiled_kernel(const float* __restrict__ feat, int64_t total_rows, int
     const int64_t r0 = tile * kFinRows;
     const int rows = (int)min((int64_t)kFinRows, total_rows - r0);
     __syncthreads();  // the previous tile has been consumed (and s_dct is complete on the first pass)
-    for (int i = threadIdx.x; i < rows * n_mels; i += blockDim.x) {
-      const int r = i / n_mels, m = i - r * n_mels;
-      float v = feat[r0 * n_mels + i];
-      if (clamp) v = fmaxf(v, group_max[((r0 + r) / frames) / rows_per_group] - top_db);
-      s_feat[r * ld + m] = v;
+    if (threadIdx.x < rows)  // one clamp floor per row (two 64-bit divisions per ROW, not per element)
+      s_floor[threadIdx.x] =
+          clamp ? group_max[((r0 + threadIdx.x) / frames) / rows_per_group] - top_db : -CUDART_INF_F;
+    __syncthreads();
+    if ((n_mels & 3) == 0) {
+      const int q4 = n_mels >> 2;  // float4 per row
+      const float4* src = reinterpret_cast<const float4*>(feat + r0 * n_mels);
+      for (int i = threadIdx.x; i < rows * q4; i += blockDim.x) {
+        const int r = i / q4, m = (i - r * q4) << 2;
+        const float4 v = __ldg(src + i);
+        const float fl = s_floor[r];
+        float* d = s_feat + r * ld + m;
+        d[0] = fmaxf(v.x, fl);
+        d[1] = fmaxf(v.y, fl);
+        d[2] = fmaxf(v.z, fl);
+        d[3] = fmaxf(v.w, fl);
+      }
+    } else {
+      for (int i = threadIdx.x; i < rows * n_mels; i += blockDim.x) {
+        const int r = i / n_mels, m = i - r * n_mels;
+        s_feat[r * ld + m] = fmaxf(feat[r0 * n_mels + i], s_floor[r]);
+      }
     }
     __syncthreads();
     float acc[4][CPT];
@@ -455,7 +473,7 @@ int mfcc_finish_impl(const b200a_frontend_desc* d, const void* ws, const float* 
   if (total == 0) return B200A_OK;
   if (d->n_mfcc <= 64) {  // register-tiled persistent kernel
     const int cpt = d->n_mfcc <= 40 ? 5 : 8;
-    const size_t tsmem = sizeof(float) * ((size_t)d->n_mels * 8 * cpt + (size_t)kFinRows * (d->n_mels + 1));
+    const size_t tsmem = sizeof(float) * ((size_t)d->n_mels * 8 * cpt + (size_t)kFinRows * (d->n_mels + 2));
     if (tsmem <= 200 * 1024) {
       auto kern = cpt == 5 ? mfcc_finish_tiled_kernel<5> : mfcc_finish_tiled_kernel<8>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)

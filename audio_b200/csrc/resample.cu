@@ -26,7 +26,7 @@ namespace b200a {
 
 namespace {
 
-constexpr int kRsWarps = 16;
+constexpr int kRsMaxWarps = 24;      // warps per CTA are chosen per ratio so the (half, group) items divide evenly
 constexpr int kRsFrames = 32;        // frames per CTA tile (two 16-row MMA tiles)
 constexpr int kRsMaxTiles = 128;     // groups of 8 phases  (new' <= 1024)
 constexpr int kRsSmemBudget = 224 * 1024;
@@ -156,6 +156,7 @@ struct RsParams {
   int64_t total_blocks;
   int xs_floats;            // floats per staging buffer
   int frag_smem_bytes;      // shared memory granted to the fragment copy (0: read them from global)
+  int row_spread;           // 1, 2 or 4: frame distance of the 8 rows one A-fragment load touches
 };
 
 // Fill one staging buffer with the samples frames [f0, f0 + 32) of `row` need:
@@ -202,7 +203,16 @@ __device__ __forceinline__ int rs_fill(const RsParams& p, int64_t row, int64_t f
   return shift;
 }
 
-__global__ void __launch_bounds__(kRsWarps * 32, 1) resample_mma_kernel(const RsParams p) {
+// Frame (0..31 within the tile) of MMA row rho (0..15) of 16-frame half h, for row spread S in {1, 2, 4}:
+// rows rho%8 of one load instruction are S frames apart; the remaining frames fill the gaps.
+__device__ __forceinline__ int frame_of(int spread, int h, int rho) {
+  const int lo = rho & 7, hi = rho >> 3;
+  if (spread == 4) return 4 * lo + hi + 2 * h;
+  if (spread == 2) return 16 * h + 2 * lo + hi;
+  return 16 * h + rho;
+}
+
+__global__ void __launch_bounds__(kRsMaxWarps * 32, 1) resample_mma_kernel(const RsParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_x = reinterpret_cast<float*>(smem_raw);                              // [2][xs_floats]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_x + 2 * (size_t)p.xs_floats);  // [2]
@@ -228,7 +238,9 @@ __global__ void __launch_bounds__(kRsWarps * 32, 1) resample_mma_kernel(const Rs
     const int64_t row = blk / p.blocks_per_row, fb = blk - row * p.blocks_per_row;
     shift[0] = rs_fill(p, row, fb * kRsFrames, s_x, s_bar + 0, tid, blockDim.x);
   }
+  __syncthreads();  // the scalar part of the first fill is visible
   const int r = lane >> 2, c = lane & 3;
+  const int n_warps = blockDim.x >> 5;
   const int n_items = 2 * p.n_tiles;  // (16-frame half, phase group)
   for (int it = 0; blk < p.total_blocks; blk += gridDim.x, ++it) {
     const int b = it & 1;
@@ -239,19 +251,23 @@ __global__ void __launch_bounds__(kRsWarps * 32, 1) resample_mma_kernel(const Rs
       shift[b ^ 1] = rs_fill(p, nrow, nfb * kRsFrames, s_x + (size_t)(b ^ 1) * p.xs_floats, s_bar + (b ^ 1), tid,
                              blockDim.x);
     }
+    // the bulk part of this tile has landed; its scalar part was written before the barrier that ended
+    // the previous iteration (or the one after the prologue fill)
     mbar_wait(s_bar + b, (it >> 1) & 1);
-    __syncthreads();  // the scalar part of the fill is visible too
 
     const int64_t row = blk / p.blocks_per_row, fb = blk - row * p.blocks_per_row;
     const int64_t f0 = fb * kRsFrames;
     const float* xs = s_x + (size_t)b * p.xs_floats + shift[b];
     float* orow = p.out + row * p.out_row_stride;
-    for (int item = warp; item < n_items; item += kRsWarps) {
+    for (int item = warp; item < n_items; item += n_warps) {
       const int half = item & 1, t = item >> 1;
       const RsTile rt = s_tiles[t];
-      // A[f][i] = xs[f*orig' + i]: rows r and r + 8 of this 16-frame half
-      const float* a_lo_row = xs + (size_t)(16 * half + r) * p.orig_r + rt.kstart + c;
-      const float* a_hi_row = a_lo_row + (size_t)8 * p.orig_r;
+      // A[f][i] = xs[f*orig' + i].  MMA row rho of 16-frame half h is frame S*(rho%8) + rho/8 + ... (see
+      // frame_of): the 8 rows one load instruction touches are S frames apart so that their 4-word windows
+      // fall into different banks (S*orig' == 4 (mod 8) words for odd orig').
+      const int fr_lo = frame_of(p.row_spread, half, r), fr_hi = frame_of(p.row_spread, half, r + 8);
+      const float* a_lo_row = xs + (size_t)fr_lo * p.orig_r + rt.kstart + c;
+      const float* a_hi_row = xs + (size_t)fr_hi * p.orig_r + rt.kstart + c;
       float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
       auto contract = [&](auto in_smem) {
         const float4* fr = (decltype(in_smem)::value ? s_frags : p.frags) + (size_t)rt.frag_off * 32 + lane;
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(kRsWarps * 32, 1) resample_mma_kernel(const Rs
       else contract(std::false_type{});
       // D rows r, r+8 = frames; columns 2c, 2c+1 = phases 8t + 2c (+1): out index = f*new' + phase
       const int j0 = 8 * t + 2 * c;
-      const int64_t m_lo = (f0 + 16 * half + r) * p.new_r + j0, m_hi = m_lo + (int64_t)8 * p.new_r;
+      const int64_t m_lo = (f0 + fr_lo) * p.new_r + j0, m_hi = (f0 + fr_hi) * p.new_r + j0;
       const float v0 = d0[0] + (d1[0] + d2[0]), v1 = d0[1] + (d1[1] + d2[1]);
       const float v2 = d0[2] + (d1[2] + d2[2]), v3 = d0[3] + (d1[3] + d2[3]);
       if (j0 < p.new_r) {
@@ -385,7 +401,30 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
       return B200A_ECUDA;
     int64_t grid = p.total_blocks < sms ? p.total_blocks : sms;
     if (grid < 1) grid = 1;
-    resample_mma_kernel<<<(unsigned)grid, kRsWarps * 32, smem, stream>>>(p);
+    // row spread: the candidate with the fewest shared-memory bank conflicts for one A-fragment load
+    // (8 rows x 4 consecutive words, rows spread*orig' words apart)
+    int best_spread = 1, best_conf = 1 << 30;
+    for (int spread = 1; spread <= 4; spread *= 2) {
+      int banks[32] = {0};
+      int worst = 0;
+      for (int rr = 0; rr < 8; ++rr)
+        for (int cc = 0; cc < 4; ++cc) {
+          const int bnk = (int)(((int64_t)rr * spread * orig_r + cc) & 31);
+          if (++banks[bnk] > worst) worst = banks[bnk];
+        }
+      if (worst < best_conf) { best_conf = worst; best_spread = spread; }
+    }
+    p.row_spread = best_spread;
+    // warps: 2 * n_tiles items per tile; prefer the largest count that divides them evenly
+    const int items = 2 * n_tiles;
+    int warps = 8;
+    double best_idle = 2.0;
+    for (int w = 8; w <= kRsMaxWarps; ++w) {
+      const int rounds = (items + w - 1) / w;
+      const double idle = 1.0 - (double)items / (double)(rounds * w);
+      if (idle <= best_idle + 1e-9) { best_idle = idle; warps = w; }  // ties go to more warps
+    }
+    resample_mma_kernel<<<(unsigned)grid, warps * 32, smem, stream>>>(p);
     return launch_status();
   }
 
