@@ -75,6 +75,7 @@ _SIGNATURES = {
         [c_void_p, c_int64, c_int64, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p],
     ),
     "b200a_fill_f32": (ctypes.c_int, [c_void_p, c_int64, c_float, c_void_p]),
+    "b200a_ratio_f32": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "b200a_resample_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "b200a_resample_prepare": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "b200a_resample_run": (

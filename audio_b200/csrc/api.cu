@@ -15,6 +15,7 @@ int pow2_prepare(const b200a_frontend_desc*, void*, size_t, cudaStream_t);
 int mfcc_finish_impl(const b200a_frontend_desc*, const void*, const float*, int64_t, int64_t, const float*, int64_t, float,
                      float*, cudaStream_t);
 int fill_impl(float*, int64_t, float, cudaStream_t);
+int ratio_impl(const float*, int64_t, float*, cudaStream_t);
 int apply_fbank_impl(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const float*, int, float*,
                      cudaStream_t);
 int amplitude_to_db_impl(const float*, int64_t, int64_t, float, float, float, float, float*, float*, cudaStream_t);
@@ -146,6 +147,13 @@ int b200a_amplitude_to_db(const float* x, int64_t groups, int64_t group_elems, f
   if (x == nullptr || out == nullptr || groups < 0 || group_elems < 0) return B200A_EINVAL;
   return amplitude_to_db_impl(x, groups, group_elems, multiplier, amin, offset, top_db, scratch, out,
                               static_cast<cudaStream_t>(stream));
+}
+
+int b200a_ratio_f32(const float* pairs, int64_t n, float* out, b200a_stream stream) {
+  if (n < 0) return B200A_EINVAL;
+  if (n == 0) return B200A_OK;
+  if (pairs == nullptr || out == nullptr) return B200A_EINVAL;
+  return ratio_impl(pairs, n, out, static_cast<cudaStream_t>(stream));
 }
 
 int b200a_fill_f32(float* dst, int64_t n, float value, b200a_stream stream) {

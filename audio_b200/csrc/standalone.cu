@@ -51,9 +51,24 @@ clamp_floor_kernel(float* __restrict__ y, int64_t group_elems, const float* __re
     yi[i] = fmaxf(yi[i], floor_v);
 }
 
+// out[i] = pairs[i][0] / pairs[i][1]  (SpectralCentroid: sum f|X| / sum |X|, functional.py:1257-1299)
+__global__ void ratio_kernel(const float2* __restrict__ pairs, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float2 v = pairs[i];
+    out[i] = v.x / v.y;
+  }
+}
+
 __global__ void fill_kernel(float* dst, int64_t n, float v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = v;
+}
+
+int ratio_impl(const float* pairs, int64_t n, float* out, cudaStream_t stream) {
+  if (n <= 0) return B200A_OK;
+  ratio_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float2*>(pairs), n, out);
+  return launch_status();
 }
 
 int fill_impl(float* dst, int64_t n, float v, cudaStream_t stream) {

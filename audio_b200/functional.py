@@ -30,6 +30,7 @@ __all__ = [
     "create_dct",
     "amplitude_to_DB",
     "resample",
+    "spectral_centroid",
     "mel_spectrogram",
     "mfcc",
 ]
@@ -232,3 +233,34 @@ def resample(
         orig_freq, new_freq, gcd, lowpass_filter_width, rolloff, resampling_method, beta, waveform.device, waveform.dtype
     )
     return _apply_sinc_resample_kernel(waveform, orig_freq, new_freq, gcd, kernel, width)
+
+
+# ---- spectral centroid (a weighted-sum epilogue of the same fused kernel) --------------
+def spectral_centroid(
+    waveform: Tensor,
+    sample_rate: int,
+    pad: int,
+    window: Tensor,
+    n_fft: int,
+    hop_length: int,
+    win_length: int,
+) -> Tensor:
+    """``(..., time) -> (..., frames)``: sum_k f_k |X_k| / sum_k |X_k| (reference functional.py:1257-1299).
+
+    The magnitude spectrogram is contracted inside the fused kernel with the two-column matrix
+    ``[bin frequency | 1]`` (the mel stage with a 2-filter bank), then one tiny kernel divides the pair.
+    """
+    _require_cuda_f32(waveform, "waveform")
+    desc = FrontendPlan.make_desc(n_fft, win_length, hop_length, pad, True, "reflect", True, False, False, 1.0, n_mels=2)
+    plan = FrontendPlan(desc)
+    dev = waveform.device
+    freqs = torch.linspace(0, sample_rate // 2, steps=1 + n_fft // 2, device=dev)
+    fb = torch.stack([freqs, torch.ones_like(freqs)], dim=1).contiguous()
+    ws = plan.workspace(window, fb, None)
+    pairs = plan.run(ws, _lib.STAGE_MEL, waveform)  # (rows, T, 2)
+    rows, frames, _ = pairs.shape
+    with torch.cuda.device(dev):
+        out = torch.empty((rows, frames), dtype=torch.float32, device=dev)
+        rc = _lib.lib().b200a_ratio_f32(pairs.data_ptr(), rows * frames, out.data_ptr(), _stream_ptr(dev))
+    _lib.check(rc, "ratio_f32")
+    return out.reshape(waveform.shape[:-1] + (frames,))

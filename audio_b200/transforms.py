@@ -23,7 +23,7 @@ from . import _lib
 from . import functional as F
 from ._plans import FrontendPlan, ResamplePlan
 
-__all__ = ["Spectrogram", "AmplitudeToDB", "MelScale", "MelSpectrogram", "MFCC", "Resample"]
+__all__ = ["Spectrogram", "AmplitudeToDB", "MelScale", "MelSpectrogram", "MFCC", "LFCC", "SpectralCentroid", "Resample"]
 
 
 class Spectrogram(torch.nn.Module):
@@ -263,6 +263,100 @@ class MFCC(torch.nn.Module):
         return F.mfcc(
             plan, mel.spectrogram.window, mel.mel_scale.fb, self.dct_mat, waveform,
             db.top_db, self.log_mels, self.process_group,
+        )
+
+
+class LFCC(torch.nn.Module):
+    r"""Linear-frequency cepstral coefficients (reference _transforms.py:712-819): the MFCC pipeline with
+    ``F.linear_fbanks`` instead of the mel bank -- same fused kernels, buffers ``filter_mat`` / ``dct_mat``."""
+
+    __constants__ = ["sample_rate", "n_filter", "n_lfcc", "dct_type", "top_db", "log_lf"]
+
+    def __init__(
+        self,
+        sample_rate: int = 16000,
+        n_filter: int = 128,
+        f_min: float = 0.0,
+        f_max: Optional[float] = None,
+        n_lfcc: int = 40,
+        dct_type: int = 2,
+        norm: str = "ortho",
+        log_lf: bool = False,
+        speckwargs: Optional[dict] = None,
+    ) -> None:
+        super().__init__()
+        supported_dct_types = [2]
+        if dct_type not in supported_dct_types:
+            raise ValueError("DCT type not supported: {}".format(dct_type))
+        self.sample_rate = sample_rate
+        self.f_min = f_min
+        self.f_max = f_max if f_max is not None else float(sample_rate // 2)
+        self.n_filter = n_filter
+        self.n_lfcc = n_lfcc
+        self.dct_type = dct_type
+        self.norm = norm
+        self.top_db = 80.0
+        self.amplitude_to_DB = AmplitudeToDB("power", self.top_db)
+        speckwargs = speckwargs or {}
+        self.Spectrogram = Spectrogram(**speckwargs)
+        if self.n_lfcc > self.Spectrogram.n_fft:
+            raise ValueError("Cannot select more LFCC coefficients than # fft bins")
+        filter_mat = F.linear_fbanks(
+            n_freqs=self.Spectrogram.n_fft // 2 + 1,
+            f_min=self.f_min,
+            f_max=self.f_max,
+            n_filter=self.n_filter,
+            sample_rate=self.sample_rate,
+        )
+        self.register_buffer("filter_mat", filter_mat)
+        dct_mat = F.create_dct(self.n_lfcc, self.n_filter, self.norm)
+        self.register_buffer("dct_mat", dct_mat)
+        self.log_lf = log_lf
+        self.process_group = None
+        self._plan: Optional[FrontendPlan] = None
+
+    def forward(self, waveform: Tensor) -> Tensor:
+        spec = self.Spectrogram
+        if spec.power is None or not spec.onesided:
+            raise RuntimeError("LFCC needs a one-sided real (power) spectrogram")
+        db = self.amplitude_to_DB
+        plan = spec._frontend_plan(self.filter_mat.shape[1], self.dct_mat.shape[1], self.log_lf)
+        plan.desc.db_multiplier, plan.desc.db_amin = float(db.multiplier), float(db.amin)
+        plan.desc.db_offset = float(db.multiplier * db.db_multiplier)
+        if self._plan is None or self._plan.desc.key() != plan.desc.key():
+            self._plan = plan
+        return F.mfcc(
+            self._plan, spec.window, self.filter_mat, self.dct_mat, waveform, db.top_db, self.log_lf, self.process_group
+        )
+
+
+class SpectralCentroid(torch.nn.Module):
+    r"""Spectral centroid per frame (reference _transforms.py:1612-1671)."""
+
+    __constants__ = ["sample_rate", "n_fft", "win_length", "hop_length", "pad"]
+
+    def __init__(
+        self,
+        sample_rate: int,
+        n_fft: int = 400,
+        win_length: Optional[int] = None,
+        hop_length: Optional[int] = None,
+        pad: int = 0,
+        window_fn: Callable[..., Tensor] = torch.hann_window,
+        wkwargs: Optional[dict] = None,
+    ) -> None:
+        super().__init__()
+        self.sample_rate = sample_rate
+        self.n_fft = n_fft
+        self.win_length = win_length if win_length is not None else n_fft
+        self.hop_length = hop_length if hop_length is not None else self.win_length // 2
+        window = window_fn(self.win_length) if wkwargs is None else window_fn(self.win_length, **wkwargs)
+        self.register_buffer("window", window)
+        self.pad = pad
+
+    def forward(self, waveform: Tensor) -> Tensor:
+        return F.spectral_centroid(
+            waveform, self.sample_rate, self.pad, self.window, self.n_fft, self.hop_length, self.win_length
         )
 
 

@@ -161,6 +161,13 @@ int b200a_amplitude_to_db(const float* x, int64_t groups, int64_t group_elems, f
 
 int b200a_fill_f32(float* dst, int64_t n, float value, b200a_stream stream);
 
+/*
+ * out[i] = pairs[i][0] / pairs[i][1].  Last step of F.spectral_centroid (functional.py:1257-1299): the
+ * fused front end is run with the two-column "filterbank" [bin frequency | 1] on the magnitude
+ * spectrogram, which yields (sum_k f_k |X_k|, sum_k |X_k|) per frame; this divides them.
+ */
+int b200a_ratio_f32(const float* pairs, int64_t n, float* out, b200a_stream stream);
+
 /* ---- polyphase sinc resampler ------------------------------------------------------------- */
 /* Workspace bytes for b200a_resample_prepare (per-phase tap supports + compacted taps). */
 size_t b200a_resample_workspace_bytes(int32_t new_r, int32_t taps);

@@ -37,6 +37,9 @@ __all__ = [
     "amplitude_to_db",
     "mel_spectrogram",
     "mfcc",
+    "linear_fbanks",
+    "lfcc",
+    "spectral_centroid",
     "sinc_resample_kernel",
     "resample_len",
     "apply_sinc_resample_kernel",
@@ -316,6 +319,41 @@ def mfcc(x, sample_rate=16000, n_mfcc=40, norm="ortho", log_mels=False, melkwarg
         feat = amplitude_to_db(mel, 10.0, 1e-10, math.log10(max(1e-10, 1.0)), 80.0)
     d = create_dct(n_mfcc, n_mels, norm) if dct is None else np.asarray(dct, dtype=np.float64)
     return np.swapaxes(np.swapaxes(feat, -1, -2) @ d, -1, -2)
+
+
+def linear_fbanks(n_freqs, f_min, f_max, n_filter, sample_rate) -> np.ndarray:
+    """functional.linear_fbanks (functional.py:590-633): the triangles of :492-515 on a linear grid."""
+    bins_hz = np.linspace(0.0, float(sample_rate // 2), n_freqs)
+    edges_hz = np.linspace(f_min, f_max, n_filter + 2)
+    widths = np.diff(edges_hz)
+    delta = edges_hz[None, :] - bins_hz[:, None]
+    return np.maximum(0.0, np.minimum(-delta[:, :-2] / widths[:-1], delta[:, 2:] / widths[1:]))
+
+
+def lfcc(x, sample_rate=16000, n_filter=128, f_min=0.0, f_max=None, n_lfcc=40, norm="ortho", log_lf=False,
+         speckwargs=None, filter_mat=None, dct=None):
+    """transforms.LFCC.forward (_transforms.py:712-819): Spectrogram -> linear filterbank -> dB (top_db 80,
+    with AmplitudeToDB's packing rule) or log -> DCT."""
+    kw = dict(speckwargs or {})
+    n_fft = kw.get("n_fft", 400)
+    win = kw.get("win_length", None) or n_fft
+    hop = kw.get("hop_length", None) or win // 2
+    spec = spectrogram(x, kw.get("pad", 0), hann_window(win), n_fft, hop, win, kw.get("power", 2.0),
+                       kw.get("normalized", False), kw.get("center", True), kw.get("pad_mode", "reflect"), True)
+    if filter_mat is None:
+        f_max = float(sample_rate // 2) if f_max is None else f_max
+        filter_mat = linear_fbanks(n_fft // 2 + 1, f_min, f_max, n_filter, sample_rate)
+    filt = np.swapaxes(np.swapaxes(spec, -1, -2) @ np.asarray(filter_mat, dtype=np.float64), -1, -2)
+    feat = np.log(filt + 1e-6) if log_lf else amplitude_to_db(filt, 10.0, 1e-10, 0.0, 80.0)
+    d = create_dct(n_lfcc, filt.shape[-2], norm) if dct is None else np.asarray(dct, dtype=np.float64)
+    return np.swapaxes(np.swapaxes(feat, -1, -2) @ d, -1, -2)
+
+
+def spectral_centroid(x, sample_rate, pad, window, n_fft, hop, win_length) -> np.ndarray:
+    """functional.spectral_centroid (functional.py:1257-1299)."""
+    spec = spectrogram(x, pad, window, n_fft, hop, win_length, 1.0, False)
+    freqs = np.linspace(0.0, float(sample_rate // 2), 1 + n_fft // 2)[:, None]
+    return (freqs * spec).sum(axis=-2) / spec.sum(axis=-2)
 
 
 # ----------------------------------------------------------------------------

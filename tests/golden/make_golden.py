@@ -76,6 +76,8 @@ def librosa_goldens():
         out[f"mfcc_{i}"] = f32(load_pt(tr, f"{pre}mfcc_{i}.pt"))
     out["power_to_db"] = f32(load_pt(tr, f"{pre}power_to_db.pt"))
     out["magnitude_to_db"] = f32(load_pt(tr, f"{pre}magnitude_to_db.pt"))
+    for i in range(3):  # test_spectral_centroid (impl.py:136-158): n_fft/hop = 400/200, 600/100, 200/50
+        out[f"spectral_centroid_{i}"] = f32(load_pt(tr, f"{pre}spectral_centroid_{i}.pt"))
     save("librosa_transforms.npz", **out)
 
     fb = {}
@@ -169,6 +171,15 @@ def reference_cases():
         mfn = T.MFCC(16000, n_mfcc=20, norm=None, melkwargs=dict(n_fft=512, hop_length=256, n_mels=64))
         out["mfcc_nonorm_out"] = f32(mfn(x))
         out["mfcc_default_out"] = f32(T.MFCC()(x))
+
+        # ---- LFCC / SpectralCentroid (same kernels, other filter matrix / epilogue) ----
+        lf = T.LFCC(16000, n_filter=64, n_lfcc=20, speckwargs=dict(n_fft=512, hop_length=128))
+        out["lfcc_filter_mat"] = f32(lf.filter_mat)
+        out["lfcc_512_out"] = f32(lf(x))
+        out["lfcc_default_out"] = f32(T.LFCC()(x[:, None]))
+        out["lfcc_log_out"] = f32(T.LFCC(16000, n_filter=40, n_lfcc=13, log_lf=True, speckwargs=dict(n_fft=1024, hop_length=256))(x))
+        out["centroid_1024_out"] = f32(T.SpectralCentroid(16000, n_fft=1024, hop_length=256)(x))
+        out["centroid_default_out"] = f32(T.SpectralCentroid(16000)(x))
 
         # ---- AmplitudeToDB stand-alone -------------------------------------------------
         p = T.Spectrogram(n_fft=400)(xs)  # (4, 201, 81)
