@@ -241,7 +241,6 @@ __global__ void __launch_bounds__(kRsMaxWarps * 32, 1) resample_mma_kernel(const
   __syncthreads();  // the scalar part of the first fill is visible
   const int r = lane >> 2, c = lane & 3;
   const int n_warps = blockDim.x >> 5;
-  const int n_items = 2 * p.n_tiles;  // (16-frame half, phase group)
   for (int it = 0; blk < p.total_blocks; blk += gridDim.x, ++it) {
     const int b = it & 1;
     const int64_t nxt = blk + gridDim.x;
@@ -259,47 +258,65 @@ __global__ void __launch_bounds__(kRsMaxWarps * 32, 1) resample_mma_kernel(const
     const int64_t f0 = fb * kRsFrames;
     const float* xs = s_x + (size_t)b * p.xs_floats + shift[b];
     float* orow = p.out + row * p.out_row_stride;
-    for (int item = warp; item < n_items; item += n_warps) {
-      const int half = item & 1, t = item >> 1;
+    for (int t = warp; t < p.n_tiles; t += n_warps) {  // one phase group, both 16-frame halves
       const RsTile rt = s_tiles[t];
-      // A[f][i] = xs[f*orig' + i].  MMA row rho of 16-frame half h is frame S*(rho%8) + rho/8 + ... (see
-      // frame_of): the 8 rows one load instruction touches are S frames apart so that their 4-word windows
-      // fall into different banks (S*orig' == 4 (mod 8) words for odd orig').
-      const int fr_lo = frame_of(p.row_spread, half, r), fr_hi = frame_of(p.row_spread, half, r + 8);
-      const float* a_lo_row = xs + (size_t)fr_lo * p.orig_r + rt.kstart + c;
-      const float* a_hi_row = xs + (size_t)fr_hi * p.orig_r + rt.kstart + c;
-      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+      // A[f][i] = xs[f*orig' + i].  MMA row rho of 16-frame half h is frame_of(S, h, rho): the 8 rows one load
+      // instruction touches are S frames apart so that their 4-word windows fall into different banks
+      // (S*orig' == 4 (mod 8) words for odd orig').
+      int fr[4];              // frames of rows (h=0: r, r+8), (h=1: r, r+8)
+      const float* arow[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        fr[q] = frame_of(p.row_spread, q >> 1, r + 8 * (q & 1));
+        arow[q] = xs + (size_t)fr[q] * p.orig_r + rt.kstart + c;
+      }
+      // per half: three independent accumulator chains (hi*hi, lo*hi, hi*lo), summed in a fixed order
+      float d[2][3][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d[h][ch][q] = 0.f;
       auto contract = [&](auto in_smem) {
-        const float4* fr = (decltype(in_smem)::value ? s_frags : p.frags) + (size_t)rt.frag_off * 32 + lane;
+        const float4* frg = (decltype(in_smem)::value ? s_frags : p.frags) + (size_t)rt.frag_off * 32 + lane;
 #pragma unroll 2
         for (int s = 0; s < rt.nsteps; ++s) {
           float4 bf;
-          if constexpr (decltype(in_smem)::value) bf = fr[(size_t)s * 32];
-          else bf = __ldg(fr + (size_t)s * 32);
-          const float av[4] = {a_lo_row[8 * s], a_hi_row[8 * s], a_lo_row[8 * s + 4], a_hi_row[8 * s + 4]};
-          uint32_t hi[4], lo[4];
+          if constexpr (decltype(in_smem)::value) bf = frg[(size_t)s * 32];
+          else bf = __ldg(frg + (size_t)s * 32);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) split_tf32(av[q], hi[q], lo[q]);
-          mma_tf32(d0, hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
-          mma_tf32(d1, lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
-          mma_tf32(d2, hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
+          for (int h = 0; h < 2; ++h) {
+            const float av[4] = {arow[2 * h][8 * s], arow[2 * h + 1][8 * s], arow[2 * h][8 * s + 4],
+                                 arow[2 * h + 1][8 * s + 4]};
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_tf32(av[q], hi[q], lo[q]);
+            mma_tf32(d[h][0], hi, __float_as_uint(bf.x), __float_as_uint(bf.y));
+            mma_tf32(d[h][1], lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
+            mma_tf32(d[h][2], hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
+          }
         }
       };
       if (frags_in_smem) contract(std::true_type{});
       else contract(std::false_type{});
-      // D rows r, r+8 = frames; columns 2c, 2c+1 = phases 8t + 2c (+1): out index = f*new' + phase
+      // D rows = frames; columns 2c, 2c+1 = phases 8t + 2c (+1): out index = f*new' + phase
       const int j0 = 8 * t + 2 * c;
-      const int64_t m_lo = (f0 + fr_lo) * p.new_r + j0, m_hi = (f0 + fr_hi) * p.new_r + j0;
-      const float v0 = d0[0] + (d1[0] + d2[0]), v1 = d0[1] + (d1[1] + d2[1]);
-      const float v2 = d0[2] + (d1[2] + d2[2]), v3 = d0[3] + (d1[3] + d2[3]);
-      if (j0 < p.new_r) {
-        if (m_lo < p.out_len) orow[m_lo] = v0;
-        if (m_hi < p.out_len) orow[m_hi] = v2;
-      }
-      if (j0 + 1 < p.new_r) {
-        if (m_lo + 1 < p.out_len) orow[m_lo + 1] = v1;
-        if (m_hi + 1 < p.out_len) orow[m_hi + 1] = v3;
-      }
+      const bool pair_ok = j0 + 1 < p.new_r && (p.new_r & 1) == 0 && (p.out_row_stride & 1) == 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int half_row = 0; half_row < 2; ++half_row) {
+          const int64_t m = (f0 + fr[2 * h + half_row]) * p.new_r + j0;
+          const float v0 = d[h][0][2 * half_row] + (d[h][1][2 * half_row] + d[h][2][2 * half_row]);
+          const float v1 = d[h][0][2 * half_row + 1] + (d[h][1][2 * half_row + 1] + d[h][2][2 * half_row + 1]);
+          if (pair_ok && m + 1 < p.out_len) {
+            *reinterpret_cast<float2*>(orow + m) = make_float2(v0, v1);  // m even, row pitch even: 8-byte aligned
+          } else {
+            if (j0 < p.new_r && m < p.out_len) orow[m] = v0;
+            if (j0 + 1 < p.new_r && m + 1 < p.out_len) orow[m + 1] = v1;
+          }
+        }
     }
     __syncthreads();  // everyone is done with buffer b before it is refilled
   }
@@ -415,8 +432,8 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
       if (worst < best_conf) { best_conf = worst; best_spread = spread; }
     }
     p.row_spread = best_spread;
-    // warps: 2 * n_tiles items per tile; prefer the largest count that divides them evenly
-    const int items = 2 * n_tiles;
+    // warps: n_tiles items (phase groups) per tile; prefer the largest count that divides them evenly
+    const int items = n_tiles;
     int warps = 8;
     double best_idle = 2.0;
     for (int w = 8; w <= kRsMaxWarps; ++w) {
