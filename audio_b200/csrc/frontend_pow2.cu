@@ -27,6 +27,10 @@
 //
 // Reference semantics: src/torchaudio/functional/functional.py:54-145 and
 // transforms/_transforms.py:403-415, :701-705 (see frontend_generic.cu for the any-size path).
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+
 #include <type_traits>
 #include <utility>
 
@@ -78,7 +82,7 @@ struct MelPlan {  // built on the device by prepare_mma_kernel
 };
 
 struct Pow2Extra {  // tables appended to the generic workspace
-  size_t tw2d, tw_eo, plan, frags, total;
+  size_t tw2d, tw_eo, plan, frags, tc_b, total;
 };
 
 inline int mel_tiles(int n_mels) { return (n_mels + 7) / 8; }
@@ -96,6 +100,8 @@ inline Pow2Extra pow2_layout(const b200a_frontend_desc& d, size_t base) {
   off = align_up(off + sizeof(MelPlan), 256);
   e.frags = off;  // worst case: every tile spans every bin
   off = align_up(off + sizeof(float4) * 32 * nt * ((n_bins + 7) / 8 + 1), 256);
+  e.tc_b = off;  // bf16 hi/lo UMMA B planes (n_fft = 256 tcgen05 path): 2 x 18 chunks x 128 rows x 16 B
+  off = align_up(off + (d.n_fft == 256 ? 2 * 18 * 128 * 16 : 0), 256);
   e.total = off;
   return e;
 }
@@ -963,6 +969,223 @@ __global__ void prepare_tw_eo_kernel(float2* tw_eo) {  // [17][32]: W_2048^(l + 
   }
 }
 
+// ================================================================================================
+// n_fft = 256 with the mel contraction on tcgen05 (5th-generation tensor cores, accumulator in TMEM).
+// At n_fft = 256 one CTA iteration finishes exactly 64 frames (8 warps x 8 frames) and 64 x 129 power
+// values fit in shared memory twice (two bf16 planes, double buffered), so the whole tile is ONE
+// tcgen05.mma M = 64, N = n_mels, K = 144 sequence issued by a single thread:
+//   transform warps   write each power value as bf16 hi + bf16 lo into two K-major, un-swizzled UMMA
+//                     operand planes (8-row x 16-byte core matrices), fence them to the async proxy and
+//                     arrive on the tile's `full` barrier
+//   contraction warp 0, lane 0   9 k-steps x (P_hi*F_hi + P_lo*F_hi + P_hi*F_lo) = 27 tcgen05.mma into 80..128
+//                     TMEM columns, tcgen05.commit -> mbarrier
+//   contraction warps 0-3   (one TMEM lane quadrant = 16 frames each) tcgen05.ld the accumulator rows,
+//                     dB / log, running top_db maximum, store.
+// Error-compensated bf16 gives ~2^-16 relative accuracy (inside the 1e-4 bar; the mma.sync TF32x3 path of
+// the larger n_fft is ~2^-21).
+// ================================================================================================
+constexpr int kTcG = 8, kTcM = 64, kTcChunks = 18;            // 18 x 8 = 144 >= 129 bins
+constexpr int kTcPlaneA = kTcChunks * kTcM * 16;               // bytes of one A plane (hi or lo)
+constexpr int kTcMaxN = 128;
+
+__device__ __forceinline__ uint16_t bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float bf16_value(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
+
+template <int POWER_MODE>
+__global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1)
+stft256_mel_tc_kernel(const Pow2Params p, const unsigned char* tc_b, int n_pad) {
+  using Ge = Geo<kTcG>;
+  constexpr int kSlots = Ge::kSlots;  // 64
+  static_assert(kSlots == kTcM, "one CTA iteration == one M = 64 tile");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* s_a = smem_raw;                                                   // [2][hi | lo] A planes
+  unsigned char* s_b = s_a + 4 * kTcPlaneA;                                        // [hi | lo] B planes, n_pad rows
+  const int plane_b = kTcChunks * n_pad * 16;
+  float2* s_tile_all = reinterpret_cast<float2*>(s_b + 2 * plane_b);               // [kWarps][kTileF2]
+  float2* s_tw = s_tile_all + kWarps * Ge::kTileF2;                                // [32][8]
+  int64_t* s_slot = reinterpret_cast<int64_t*>(s_tw + 32 * kTcG);                  // [2][64]
+  int64_t* s_grp = s_slot + 2 * kSlots;                                            // [2][64]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + 2 * kSlots);               // [kWarps] staging
+  uint64_t* s_full = s_bar + kWarps;                                               // [2]
+  uint64_t* s_empty = s_full + 2;                                                  // [2]
+  uint64_t* s_mma = s_empty + 2;                                                   // [1]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mma + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 32 * kTcG; i += blockDim.x) s_tw[i] = p.tw2d[i];
+  {  // A planes start as zeros (chunk 16 beyond bin 128 and chunk 17 stay zero), B planes come prepared
+    uint4* a4 = reinterpret_cast<uint4*>(s_a);
+    for (int i = tid; i < 4 * kTcPlaneA / 16; i += blockDim.x) a4[i] = make_uint4(0, 0, 0, 0);
+    const uint4* src = reinterpret_cast<const uint4*>(tc_b);
+    uint4* b4 = reinterpret_cast<uint4*>(s_b);
+    for (int i = tid; i < 2 * plane_b / 16; i += blockDim.x) b4[i] = src[i];
+  }
+  if (tid < kWarps) mbar_init(s_bar + tid, 1);
+  if (tid == 0) {
+    mbar_init(s_full + 0, kWarps);
+    mbar_init(s_full + 1, kWarps);
+    mbar_init(s_empty + 0, kMelWarps);
+    mbar_init(s_empty + 1, kMelWarps);
+    mbar_init(s_mma, 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand planes -> visible to the tensor core
+  __syncthreads();
+
+  const int64_t stride = (int64_t)gridDim.x * kWarps;
+  const int64_t u0 = (int64_t)blockIdx.x * kWarps;
+  const int width = p.n_mels;
+
+  if (warp < kWarps) {
+    // =============================== transform warps ===========================================
+    reg_alloc<kFftRegs>();
+    float2* tile = s_tile_all + warp * Ge::kTileF2;
+    float* stage = reinterpret_cast<float*>(tile);
+    uint64_t* bar = s_bar + warp;
+    float wreg[32];
+    load_window<kTcG>(p, lane, wreg);
+    const int half = p.center ? Ge::kNfft / 2 : 0;
+    const int gi = lane / kTcG, l = lane % kTcG;
+    uint32_t parity = 0;
+    bool staged = false;
+    UnitCursor cur;
+    cur.init(u0 + warp, stride, p.units_per_row);
+    if (bulk_eligible<kTcG>(p, half, cur.u, cur.ub)) {
+      if (lane == 0) issue_bulk<kTcG>(p, half, cur.row, cur.ub, stage, bar);
+      staged = true;
+    }
+    int it = 0;
+    for (int64_t base = u0; base < p.total_units; base += stride, ++it, cur.advance()) {
+      const bool valid = cur.u < p.total_units;
+      float pa[17], pb[17];
+      if (valid)
+        transform_unit<POWER_MODE, kTcG, -1, true>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
+                                                   pb);
+      const int b = it & 1;
+      if (it >= 2) mbar_wait(s_empty + b, ((it >> 1) & 1) ^ 1);  // the tensor core has consumed this buffer
+      const int row_a = Ge::kFrames * warp + 2 * gi;             // tile rows of this lane group's two frames
+      unsigned char* hi_a = s_a + (size_t)b * 2 * kTcPlaneA + row_a * 16 + l * 2;
+      unsigned char* lo_a = hi_a + kTcPlaneA;
+      if (valid) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {  // bin l + 8 m = chunk m, position l
+          const uint16_t ha = bf16_bits(pa[m]), hb = bf16_bits(pb[m]);
+          *reinterpret_cast<uint16_t*>(hi_a + m * (kTcM * 16)) = ha;
+          *reinterpret_cast<uint16_t*>(hi_a + m * (kTcM * 16) + 16) = hb;
+          *reinterpret_cast<uint16_t*>(lo_a + m * (kTcM * 16)) = bf16_bits(pa[m] - bf16_value(ha));
+          *reinterpret_cast<uint16_t*>(lo_a + m * (kTcM * 16) + 16) = bf16_bits(pb[m] - bf16_value(hb));
+        }
+        if (l == 0) {  // bin 128 = chunk 16, position 0
+          const uint16_t ha = bf16_bits(pa[16]), hb = bf16_bits(pb[16]);
+          *reinterpret_cast<uint16_t*>(hi_a + 16 * (kTcM * 16)) = ha;
+          *reinterpret_cast<uint16_t*>(hi_a + 16 * (kTcM * 16) + 16) = hb;
+          *reinterpret_cast<uint16_t*>(lo_a + 16 * (kTcM * 16)) = bf16_bits(pa[16] - bf16_value(ha));
+          *reinterpret_cast<uint16_t*>(lo_a + 16 * (kTcM * 16) + 16) = bf16_bits(pb[16] - bf16_value(hb));
+        }
+      }
+      if (l == 0) {
+        const int64_t ta = cur.ub * Ge::kFrames + 2 * gi;
+        const int64_t oa = (cur.row * p.frames + ta) * (int64_t)width;
+        s_slot[b * kSlots + row_a] = (valid && ta < p.frames) ? oa : -1;
+        s_slot[b * kSlots + row_a + 1] = (valid && ta + 1 < p.frames) ? oa + width : -1;
+        const int64_t g = cur.row / p.rows_per_group;
+        s_grp[b * kSlots + row_a] = g;
+        s_grp[b * kSlots + row_a + 1] = g;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my plane writes -> async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_full + b);
+    }
+  } else {
+    // =============================== contraction warps =========================================
+    reg_dealloc<kMelRegs>();
+    const int mw = warp - kWarps;  // TMEM lane quadrant == warp % 4
+    if (mw == 0) tmem_alloc(s_tmem, 128);
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"n"(kMelWarps * 32) : "memory");
+    tc_fence_after();
+    const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+    GroupMax gmax{p.stage == B200A_STAGE_FEAT ? p.group_max : nullptr, -1, -CUDART_INF_F};
+    const uint32_t idesc = umma_idesc_bf16(kTcM, n_pad);
+    const uint32_t b_hi_addr = smem_u32(s_b), b_lo_addr = b_hi_addr + plane_b;
+    const uint32_t b_lbo = (uint32_t)n_pad * 16;
+    int it = 0;
+    for (int64_t base = u0; base < p.total_units; base += stride, ++it) {
+      const int b = it & 1;
+      mbar_wait(s_full + b, (it >> 1) & 1);
+      tc_fence_after();
+      if (mw == 0 && lane == 0) {
+        const uint32_t a_hi_addr = smem_u32(s_a + (size_t)b * 2 * kTcPlaneA), a_lo_addr = a_hi_addr + kTcPlaneA;
+#pragma unroll 1
+        for (int s = 0; s < kTcChunks / 2; ++s) {  // K = 16 per MMA = two 16-byte chunks
+          const uint64_t ah = umma_smem_desc(a_hi_addr + s * 2 * kTcM * 16, kTcM * 16, 128);
+          const uint64_t al = umma_smem_desc(a_lo_addr + s * 2 * kTcM * 16, kTcM * 16, 128);
+          const uint64_t bh = umma_smem_desc(b_hi_addr + s * 2 * b_lbo, b_lbo, 128);
+          const uint64_t bl = umma_smem_desc(b_lo_addr + s * 2 * b_lbo, b_lbo, 128);
+          umma_bf16(tmem_d, ah, bh, idesc, s > 0 ? 1u : 0u);
+          umma_bf16(tmem_d, al, bh, idesc, 1u);
+          umma_bf16(tmem_d, ah, bl, idesc, 1u);
+        }
+        umma_commit(s_mma);
+      }
+      mbar_wait(s_mma, it & 1);  // accumulator complete, operand planes of buffer b no longer read
+      tc_fence_after();
+      // epilogue: thread i < 16 of quadrant mw owns tile row 16 mw + i == TMEM lane 32 mw + i
+      const int row = 16 * mw + (lane & 15);
+      const int64_t o = s_slot[b * kSlots + row];
+      const int64_t g = s_grp[b * kSlots + row];
+      const bool row_ok = lane < 16 && o >= 0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty + b);
+#pragma unroll 1
+      for (int c0 = 0; c0 < n_pad; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(32 * mw) << 16) + (uint32_t)c0, v);
+        if (p.stage == B200A_STAGE_FEAT) {
+          float mx = -CUDART_INF_F;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            v[q] = p.log_mels ? logf(v[q] + 1e-6f) : p.db_mult * log10f(fmaxf(v[q], p.db_amin)) - p.db_offset;
+            if (c0 + q < p.n_mels) mx = fmaxf(mx, v[q]);
+          }
+          gmax.add(g, mx, row_ok);
+        }
+        if (row_ok) {
+          float* dst = p.out + o + c0;
+          if ((width & 3) == 0 && c0 + 16 <= p.n_mels) {
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (c0 + q < p.n_mels) dst[q] = v[q];
+          }
+        }
+      }
+      tc_fence_before();  // my tcgen05.ld are done before the next tile's MMAs overwrite the accumulator
+      asm volatile("bar.sync 1, %0;" ::"n"(kMelWarps * 32) : "memory");
+      tc_fence_after();
+    }
+    gmax.flush();
+    if (mw == 0) tmem_dealloc(tmem_d, 128);
+  }
+}
+
+// filterbank -> bf16 hi / lo UMMA B planes: B[n][k] = fb[k][n], K-major un-swizzled, n_pad rows, 144 columns
+__global__ void prepare_tc_b_kernel(const float* __restrict__ fb, int n_bins, int n_mels, int n_pad,
+                                    unsigned char* planes) {
+  const int plane = kTcChunks * n_pad * 16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad * kTcChunks * 8; i += gridDim.x * blockDim.x) {
+    const int n = i / (kTcChunks * 8), k = i - n * (kTcChunks * 8);
+    const float v = (n < n_mels && k < n_bins) ? fb[(size_t)k * n_mels + n] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(h));
+    const size_t off = (size_t)(k >> 3) * n_pad * 16 + (size_t)n * 16 + (size_t)(k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(planes + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(planes + plane + off) = lo;
+  }
+}
+
 // ---- table preparation ------------------------------------------------------------------------
 __global__ void prepare_tw2d_kernel(float2* tw2d, int G) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = k2 * G + g
@@ -1036,6 +1259,16 @@ static_assert(kMaxItemsPerWarp * kMelWarps >= kMaxItems,
 
 }  // namespace
 
+// n_fft = 256 mel stages run their contraction on tcgen05 unless B200A_TC256=0 asks for the mma.sync path
+static int tc_n_pad(int n_mels) { return (n_mels + 15) / 16 * 16; }
+static bool tc256_applicable(const b200a_frontend_desc& d) {
+  static const bool enabled = [] {
+    const char* e = std::getenv("B200A_TC256");
+    return !(e && e[0] == '0');
+  }();
+  return enabled && d.n_fft == 256 && d.onesided && d.n_mels > 0 && tc_n_pad(d.n_mels) <= kTcMaxN;
+}
+
 size_t pow2_workspace_extra(const b200a_frontend_desc* d) {
   if (!pow2_applicable(*d)) return 0;
   const size_t base = ws_layout(*d).total;
@@ -1056,6 +1289,11 @@ int pow2_prepare(const b200a_frontend_desc* d, void* ws, size_t ws_bytes, cudaSt
                                               reinterpret_cast<const int2*>(base + l.bands), d->n_fft / 2 + 1, d->n_mels,
                                               mel_tiles(d->n_mels), reinterpret_cast<MelPlan*>(base + e.plan),
                                               reinterpret_cast<float4*>(base + e.frags));
+  }
+  if (tc256_applicable(*d)) {
+    const int n_pad = tc_n_pad(d->n_mels);
+    prepare_tc_b_kernel<<<(n_pad * kTcChunks * 8 + 255) / 256, 256, 0, stream>>>(
+        reinterpret_cast<const float*>(base + l.fb), d->n_fft / 2 + 1, d->n_mels, n_pad, base + e.tc_b);
   }
   return launch_status();
 }
@@ -1109,6 +1347,23 @@ static int launch_mel(const Pow2Params& p, cudaStream_t stream) {
   const int64_t grid = persistent_grid(p);
   if (grid < 0) return B200A_ECUDA;
   kern<<<(unsigned)grid, (kWarps + kMelWarps) * 32, smem, stream>>>(p);
+  return launch_status();
+}
+
+template <int POWER_MODE>
+static int launch_tc256(const Pow2Params& p, const unsigned char* tc_b, cudaStream_t stream) {
+  using Ge = Geo<kTcG>;
+  const int n_pad = tc_n_pad(p.n_mels);
+  const size_t smem = 4 * (size_t)kTcPlaneA + 2 * (size_t)kTcChunks * n_pad * 16 +
+                      sizeof(float2) * (kWarps * Ge::kTileF2 + 32 * kTcG) + sizeof(int64_t) * 4 * Ge::kSlots +
+                      sizeof(uint64_t) * (kWarps + 5) + 16;
+  if (smem > 227 * 1024) return B200A_EUNSUPPORTED;
+  auto kern = stft256_mel_tc_kernel<POWER_MODE>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return B200A_ECUDA;
+  const int64_t grid = persistent_grid(p);
+  if (grid < 0) return B200A_ECUDA;
+  kern<<<(unsigned)grid, (kWarps + kMelWarps) * 32, smem, stream>>>(p, tc_b, n_pad);
   return launch_status();
 }
 
@@ -1201,6 +1456,8 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
     const float2* tw_eo = reinterpret_cast<const float2*>(base + e.tw_eo);
     return d->power == 2.f ? launch_eo<2>(p, tw_eo, mel, stream) : launch_eo<0>(p, tw_eo, mel, stream);
   }
+  if (mel && tc256_applicable(*d))
+    return d->power == 2.f ? launch_tc256<2>(p, base + e.tc_b, stream) : launch_tc256<0>(p, base + e.tc_b, stream);
   return d->power == 2.f ? launch_any<2>(p, d->n_fft, mel, stream) : launch_any<0>(p, d->n_fft, mel, stream);
 }
 
