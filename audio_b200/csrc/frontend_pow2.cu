@@ -82,7 +82,7 @@ struct MelPlan {  // built on the device by prepare_mma_kernel
 };
 
 struct Pow2Extra {  // tables appended to the generic workspace
-  size_t tw2d, tw_eo, plan, frags, tc_b, total;
+  size_t tw2d, tw_eo, plan, frags, tc_plan, tc_b, total;
 };
 
 inline int mel_tiles(int n_mels) { return (n_mels + 7) / 8; }
@@ -100,8 +100,11 @@ inline Pow2Extra pow2_layout(const b200a_frontend_desc& d, size_t base) {
   off = align_up(off + sizeof(MelPlan), 256);
   e.frags = off;  // worst case: every tile spans every bin
   off = align_up(off + sizeof(float4) * 32 * nt * ((n_bins + 7) / 8 + 1), 256);
-  e.tc_b = off;  // bf16 hi/lo UMMA B planes (n_fft = 256 tcgen05 path): 2 x 18 chunks x 128 rows x 16 B
-  off = align_up(off + (d.n_fft == 256 ? 2 * 18 * 128 * 16 : 0), 256);
+  const bool tc = d.n_mels > 0 && d.n_fft <= 1024;  // tcgen05 contraction: step table + banded bf16 B blocks
+  e.tc_plan = off;
+  off = align_up(off + (tc ? 1024 : 0), 256);
+  e.tc_b = off;
+  off = align_up(off + (tc ? 96 * 1024 : 0), 256);
   e.total = off;
   return e;
 }
@@ -198,6 +201,8 @@ struct Pow2Params {
   const MelPlan* plan;
   const float4* frags;   // [steps][32] (b0_hi, b1_hi, b0_lo, b1_lo) in mma B-fragment order
   const WsHeader* hdr;
+  const struct TcPlan* tc;     // tcgen05 contraction plan (nullptr: not available for this size)
+  const unsigned char* tc_b;   // its banded bf16 B blocks
   int hop, pad, center, pad_mode, n_mels;
   int stage, log_mels, bulk_ok;
   float power, db_mult, db_amin, db_offset;
@@ -441,18 +446,18 @@ __device__ __forceinline__ void load_window(const Pow2Params& p, int lane, float
 // ------------------------------------------------------------------------------------------------
 // Spectrogram kernel: 8 independent warps, power spectra straight to global memory.
 // ------------------------------------------------------------------------------------------------
-template <int POWER_MODE, int G, int HG>
-__global__ void __launch_bounds__(kWarps * 32, 1) stft_pow2_power_kernel(const Pow2Params p) {
+template <int POWER_MODE, int G, int HG, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) stft_pow2_power_kernel(const Pow2Params p) {
   using Ge = Geo<G>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* s_tw = reinterpret_cast<float2*>(smem_raw);                                    // [32][G]
-  float2* s_tile_all = s_tw + 32 * 32;                                                   // [kWarps][kTileF2]
-  float* s_stage_all = reinterpret_cast<float*>(s_tile_all + kWarps * Ge::kTileF2);      // [kWarps][kStageFloats]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage_all + kWarps * Ge::kStageFloats);  // [kWarps]
+  float2* s_tile_all = s_tw + 32 * 32;                                                   // [NW][kTileF2]
+  float* s_stage_all = reinterpret_cast<float*>(s_tile_all + NW * Ge::kTileF2);      // [NW][kStageFloats]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage_all + NW * Ge::kStageFloats);  // [NW]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 32 * G; i += blockDim.x) s_tw[i] = p.tw2d[i];
-  if (tid < kWarps) mbar_init(s_bar + tid, 1);
+  if (tid < NW) mbar_init(s_bar + tid, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
@@ -466,7 +471,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) stft_pow2_power_kernel(const P
   uint32_t parity = 0;
   bool staged = false;
   UnitCursor cur;
-  cur.init((int64_t)blockIdx.x * kWarps + warp, (int64_t)gridDim.x * kWarps, p.units_per_row);
+  cur.init((int64_t)blockIdx.x * NW + warp, (int64_t)gridDim.x * NW, p.units_per_row);
   if (bulk_eligible<G>(p, half, cur.u, cur.ub)) {
     if (lane == 0) issue_bulk<G>(p, half, cur.row, cur.ub, stage, bar);
     staged = true;
@@ -567,10 +572,9 @@ __device__ __forceinline__ void contract_tile(const Pow2Params& p, const MelPlan
 constexpr int kFftRegs = 200, kMelRegs = 96;  // 256*200 + 128*96 = 63488 <= 64512 = 384 * 168
 
 template <int POWER_MODE, int G, int HG>
-__global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft_pow2_mel_kernel(const Pow2Params p) {
+__device__ __forceinline__ void mel_body_mma(const Pow2Params& p, unsigned char* smem_raw) {
   using Ge = Geo<G>;
   constexpr int kSlots = Ge::kSlots, kPitch = Ge::kPitch;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* s_tw = reinterpret_cast<float2*>(smem_raw);                              // [32][G]
   float2* s_tile_all = s_tw + 32 * 32;                                             // [kWarps][kTileF2] (also staging)
   float* s_pow = reinterpret_cast<float*>(s_tile_all + kWarps * Ge::kTileF2);      // [2][kSlots][kPitch]
@@ -673,7 +677,7 @@ __global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft_pow2_mel_ke
     int it = 0;
     for (int64_t base = u0; base < p.total_units; base += stride, ++it) {
       const int b = it & 1;
-      mbar_wait(s_full + b, (it >> 1) & 1);
+      mbar_wait_relaxed(s_full + b, (it >> 1) & 1);
 #pragma unroll 1
       for (int mt = 0; mt < kSlots / 16; ++mt)  // 16-frame MMA tiles of this iteration
         contract_tile<kPitch>(p, s_plan, s_frags, frags_in_smem, mw, lane, s_pow + (size_t)(b * kSlots + 16 * mt) * kPitch,
@@ -970,55 +974,125 @@ __global__ void prepare_tw_eo_kernel(float2* tw_eo) {  // [17][32]: W_2048^(l + 
 }
 
 // ================================================================================================
-// n_fft = 256 with the mel contraction on tcgen05 (5th-generation tensor cores, accumulator in TMEM).
-// At n_fft = 256 one CTA iteration finishes exactly 64 frames (8 warps x 8 frames) and 64 x 129 power
-// values fit in shared memory twice (two bf16 planes, double buffered), so the whole tile is ONE
-// tcgen05.mma M = 64, N = n_mels, K = 144 sequence issued by a single thread:
-//   transform warps   write each power value as bf16 hi + bf16 lo into two K-major, un-swizzled UMMA
-//                     operand planes (8-row x 16-byte core matrices), fence them to the async proxy and
-//                     arrive on the tile's `full` barrier
-//   contraction warp 0, lane 0   9 k-steps x (P_hi*F_hi + P_lo*F_hi + P_hi*F_lo) = 27 tcgen05.mma into 80..128
-//                     TMEM columns, tcgen05.commit -> mbarrier
-//   contraction warps 0-3   (one TMEM lane quadrant = 16 frames each) tcgen05.ld the accumulator rows,
-//                     dB / log, running top_db maximum, store.
-// Error-compensated bf16 gives ~2^-16 relative accuracy (inside the 1e-4 bar; the mma.sync TF32x3 path of
-// the larger n_fft is ~2^-21).
+// Mel contraction on tcgen05 (5th-generation tensor cores, accumulator in tensor memory).
+//
+// One CTA iteration finishes R = 16 / 32 / 64 frames (n_fft = 1024 / 512 / 256).  Three roles:
+//   transform warps 0-7   publish fp32 power rows into the double-buffered shared tile (as in the
+//                         mma.sync body) and arrive on the tile's `full` barrier
+//   operand warps 8-11    split every power value into bf16 hi + bf16 lo and write the two K-major,
+//                         un-swizzled UMMA operand planes (8-row x 16-byte core matrices; chunk = 8 bins,
+//                         R rows per chunk), fence them to the async proxy, release the fp32 tile
+//   warp 8                issues, per k-step of 16 bins,
+//                             D[:, n0:n0+N] += P_hi F_hi + P_lo F_hi + P_hi F_lo   (tcgen05.mma kind::f16, M = 64)
+//                         into n_mels TMEM columns and commits to an mbarrier.  The filterbank sits in
+//                         shared memory as BANDED UMMA B blocks: for each k-step only the filters that are
+//                         non-zero there (rounded to groups of 8), bf16 hi + lo.  Tile rows >= R of the
+//                         M = 64 instruction alias whatever follows in shared memory and land in TMEM
+//                         lanes nobody reads (an accumulator row depends on its own operand row only).
+//   epilogue warps        R/16 of the four (one TMEM lane quadrant each) tcgen05.ld their 16 frames,
+//                         apply dB / log, track the top_db maximum and store.
+// Error-compensated bf16 carries ~2^-16 relative error per product (the 1e-4 bar; the TF32x3 mma.sync body
+// ~2^-21); the contraction costs the SM ~1.5 k issue slots per tile instead of ~4.4 k.
 // ================================================================================================
-constexpr int kTcG = 8, kTcM = 64, kTcChunks = 18;            // 18 x 8 = 144 >= 129 bins
-constexpr int kTcPlaneA = kTcChunks * kTcM * 16;               // bytes of one A plane (hi or lo)
-constexpr int kTcMaxN = 128;
+constexpr int kTcFftRegs = 216, kTcEpiRegs = 72;  // 256*216 + 128*72 = 64512 = 384 * 168
+constexpr int kTcMaxSteps = 34;       // k-steps of 16 bins (n_fft = 1024: 33)
+constexpr int kTcMaxN = 128;          // filters: 2 accumulator columns each, two accumulators in 512 TMEM columns
+constexpr int kTcWsBBytes = 96 * 1024;  // workspace reserved for the banded B blocks
 
-__device__ __forceinline__ uint16_t bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
-__device__ __forceinline__ float bf16_value(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
+struct TcStep {
+  uint32_t b_off;  // byte offset of the step's block in the B region (64 n bytes: 2 k-chunks x 2 n operand rows)
+  uint32_t n;      // filters covered (multiple of 8)
+  uint32_t col;    // first accumulator column == first filter
+  uint32_t kstep;  // which 16 bins: [16 kstep, 16 kstep + 16)
+};
+struct TcPlan {  // built on the device by prepare_tc_kernel
+  int ok, steps, n_pad, b_bytes;
+  TcStep step[kTcMaxSteps];
+};
+struct __align__(16) TcIssue {  // ready-to-issue descriptors of one k-step, built per CTA
+  uint64_t a_hi, a_lo, b;
+  uint32_t idesc, col;
+};
 
-template <int POWER_MODE>
-__global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1)
-stft256_mel_tc_kernel(const Pow2Params p, const unsigned char* tc_b, int n_pad) {
-  using Ge = Geo<kTcG>;
-  constexpr int kSlots = Ge::kSlots;  // 64
-  static_assert(kSlots == kTcM, "one CTA iteration == one M = 64 tile");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* s_a = smem_raw;                                                   // [2][hi | lo] A planes
-  unsigned char* s_b = s_a + 4 * kTcPlaneA;                                        // [hi | lo] B planes, n_pad rows
-  const int plane_b = kTcChunks * n_pad * 16;
-  float2* s_tile_all = reinterpret_cast<float2*>(s_b + 2 * plane_b);               // [kWarps][kTileF2]
-  float2* s_tw = s_tile_all + kWarps * Ge::kTileF2;                                // [32][8]
-  int64_t* s_slot = reinterpret_cast<int64_t*>(s_tw + 32 * kTcG);                  // [2][64]
-  int64_t* s_grp = s_slot + 2 * kSlots;                                            // [2][64]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + 2 * kSlots);               // [kWarps] staging
-  uint64_t* s_full = s_bar + kWarps;                                               // [2]
-  uint64_t* s_empty = s_full + 2;                                                  // [2]
-  uint64_t* s_mma = s_empty + 2;                                                   // [1]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mma + 1);
+template <int G>
+struct TcGeo {
+  using Ge = Geo<G>;
+  static constexpr int kRows = Ge::kSlots;                 // real frames per tile
+  static constexpr int kChunks = 2 * G + 2;                // ceil((16 G + 1) / 8) rounded up to even
+  static constexpr int kSteps = kChunks / 2;
+  static constexpr int kPlane = kChunks * kRows * 16;      // bytes of one operand plane
+  static constexpr int kEpi = kRows / 16;                  // epilogue warps == TMEM lane quadrants in use
+  static constexpr int kPowBytes = 2 * kRows * Ge::kPitch * 4;
+  static constexpr int kFixed = 2 * kPlane + kPowBytes + 8 * (kWarps * Ge::kTileF2 + 32 * G) + 32 * kRows +
+                                (int)sizeof(TcIssue) * kTcMaxSteps + 8 * (kWarps + 8) + 16;
+  static constexpr int kBBudget = ((227 * 1024 - kFixed) / 128) * 128;
+  static_assert(kSteps <= kTcMaxSteps && kRows <= 64, "one M = 64 tile per iteration");
+  static_assert(Ge::kPitch >= 8 * (kChunks - 1), "the last real chunk reads 8 floats of a power row");
+};
+inline int tc_b_budget(int n_fft) {
+  return n_fft == 1024 ? TcGeo<32>::kBBudget : (n_fft == 512 ? TcGeo<16>::kBBudget : TcGeo<8>::kBBudget);
+}
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 32 * kTcG; i += blockDim.x) s_tw[i] = p.tw2d[i];
-  {  // A planes start as zeros (chunk 16 beyond bin 128 and chunk 17 stay zero), B planes come prepared
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+// (x, y) -> packed bf16 pair (x in the low half) and the packed pair of the residuals
+__device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));
+  const float rx = x - __uint_as_float(hi << 16), ry = y - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(ry), "f"(rx));
+}
+
+template <int POWER_MODE, int G, int HG>
+__device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* smem_raw) {
+  using Ge = Geo<G>;
+  using Tc = TcGeo<G>;
+  constexpr int kRows = Tc::kRows, kPlane = Tc::kPlane, kEpi = Tc::kEpi, kPitch = Ge::kPitch;
+  unsigned char* s_a = smem_raw;                                                   // [hi | lo] operand planes
+  unsigned char* s_b = s_a + 2 * kPlane;                                           // banded B blocks
+  float* s_pow = reinterpret_cast<float*>(s_b + Tc::kBBudget);                     // [2][kRows][kPitch]
+  float2* s_tile_all = reinterpret_cast<float2*>(s_pow + 2 * kRows * kPitch);      // [kWarps][kTileF2]
+  float2* s_tw = s_tile_all + kWarps * Ge::kTileF2;                                // [32][G]
+  int64_t* s_slot = reinterpret_cast<int64_t*>(s_tw + 32 * G);                     // [2][kRows]
+  int64_t* s_grp = s_slot + 2 * kRows;                                             // [2][kRows]
+  TcIssue* s_issue = reinterpret_cast<TcIssue*>(s_grp + 2 * kRows);                // [kTcMaxSteps]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_issue + kTcMaxSteps);            // [kWarps] staging
+  uint64_t* s_full = s_bar + kWarps;                                               // [2] fp32 tile published
+  uint64_t* s_empty = s_full + 2;                                                  // [2] fp32 tile converted
+  uint64_t* s_ready = s_empty + 2;                                                 // [1] operand planes written
+  uint64_t* s_mma = s_ready + 1;                                                   // [1] accumulator complete
+  uint64_t* s_tfree = s_mma + 1;                                                   // [2] accumulator read out
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_tfree + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+  const int n_steps = p.tc->steps, n_pad = p.tc->n_pad;
+  for (int i = tid; i < 32 * G; i += blockDim.x) s_tw[i] = p.tw2d[i];
+  {  // operand planes start as zeros (the chunk beyond n_fft/2 stays zero), B blocks come prepared
     uint4* a4 = reinterpret_cast<uint4*>(s_a);
-    for (int i = tid; i < 4 * kTcPlaneA / 16; i += blockDim.x) a4[i] = make_uint4(0, 0, 0, 0);
-    const uint4* src = reinterpret_cast<const uint4*>(tc_b);
+    for (int i = tid; i < 2 * kPlane / 16; i += blockDim.x) a4[i] = make_uint4(0, 0, 0, 0);
+    const uint4* src = reinterpret_cast<const uint4*>(p.tc_b);
     uint4* b4 = reinterpret_cast<uint4*>(s_b);
-    for (int i = tid; i < 2 * plane_b / 16; i += blockDim.x) b4[i] = src[i];
+    const int n16 = p.tc->b_bytes / 16;
+    for (int i = tid; i < n16; i += blockDim.x) b4[i] = src[i];
+  }
+  // columns >= n_bins of every power row are read by the last chunk: keep them zero
+  for (int i = tid; i < 2 * kRows * (kPitch - Ge::kBins); i += blockDim.x) {
+    const int r = i / (kPitch - Ge::kBins), c = i - r * (kPitch - Ge::kBins);
+    s_pow[r * kPitch + Ge::kBins + c] = 0.f;
+  }
+  if (tid < n_steps) {
+    const TcStep st = p.tc->step[tid];
+    const uint32_t hi = smem_u32(s_b) + st.b_off, a_addr = smem_u32(s_a) + st.kstep * 2 * kRows * 16;
+    TcIssue o;
+    o.a_hi = umma_smem_desc(a_addr, kRows * 16, 128);
+    o.a_lo = umma_smem_desc(a_addr + kPlane, kRows * 16, 128);
+    o.b = umma_smem_desc(hi, st.n * 32, 128);      // 2 n operand rows: per 8 filters, 8 hi rows then 8 lo rows
+    o.idesc = umma_idesc_bf16(64, 2 * (int)st.n);
+    o.col = 2 * st.col;                            // filter f: columns 16 (f / 8) + f % 8 (x F_hi) and + 8 (x F_lo)
+    s_issue[tid] = o;
   }
   if (tid < kWarps) mbar_init(s_bar + tid, 1);
   if (tid == 0) {
@@ -1026,10 +1100,13 @@ stft256_mel_tc_kernel(const Pow2Params p, const unsigned char* tc_b, int n_pad) 
     mbar_init(s_full + 1, kWarps);
     mbar_init(s_empty + 0, kMelWarps);
     mbar_init(s_empty + 1, kMelWarps);
+    mbar_init(s_ready, kMelWarps);
     mbar_init(s_mma, 1);
+    mbar_init(s_tfree + 0, kEpi);
+    mbar_init(s_tfree + 1, kEpi);
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand planes -> visible to the tensor core
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // B blocks, zeroed planes -> the tensor core
   __syncthreads();
 
   const int64_t stride = (int64_t)gridDim.x * kWarps;
@@ -1038,20 +1115,20 @@ stft256_mel_tc_kernel(const Pow2Params p, const unsigned char* tc_b, int n_pad) 
 
   if (warp < kWarps) {
     // =============================== transform warps ===========================================
-    reg_alloc<kFftRegs>();
+    reg_alloc<kTcFftRegs>();
     float2* tile = s_tile_all + warp * Ge::kTileF2;
     float* stage = reinterpret_cast<float*>(tile);
     uint64_t* bar = s_bar + warp;
     float wreg[32];
-    load_window<kTcG>(p, lane, wreg);
+    load_window<G>(p, lane, wreg);
     const int half = p.center ? Ge::kNfft / 2 : 0;
-    const int gi = lane / kTcG, l = lane % kTcG;
+    const int gi = lane / G, l = lane % G;
     uint32_t parity = 0;
     bool staged = false;
     UnitCursor cur;
     cur.init(u0 + warp, stride, p.units_per_row);
-    if (bulk_eligible<kTcG>(p, half, cur.u, cur.ub)) {
-      if (lane == 0) issue_bulk<kTcG>(p, half, cur.row, cur.ub, stage, bar);
+    if (bulk_eligible<G>(p, half, cur.u, cur.ub)) {
+      if (lane == 0) issue_bulk<G>(p, half, cur.row, cur.ub, stage, bar);
       staged = true;
     }
     int it = 0;
@@ -1059,131 +1136,238 @@ stft256_mel_tc_kernel(const Pow2Params p, const unsigned char* tc_b, int n_pad) 
       const bool valid = cur.u < p.total_units;
       float pa[17], pb[17];
       if (valid)
-        transform_unit<POWER_MODE, kTcG, -1, true>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
-                                                   pb);
+        transform_unit<POWER_MODE, G, HG, true>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
+                                                pb);
       const int b = it & 1;
-      if (it >= 2) mbar_wait(s_empty + b, ((it >> 1) & 1) ^ 1);  // the tensor core has consumed this buffer
-      const int row_a = Ge::kFrames * warp + 2 * gi;             // tile rows of this lane group's two frames
-      unsigned char* hi_a = s_a + (size_t)b * 2 * kTcPlaneA + row_a * 16 + l * 2;
-      unsigned char* lo_a = hi_a + kTcPlaneA;
+      if (it >= 2) mbar_wait(s_empty + b, ((it >> 1) & 1) ^ 1);  // the operand warps have converted this buffer
+      const int slot_a = Ge::kFrames * warp + 2 * gi;
+      float* prow_a = s_pow + (size_t)(b * kRows + slot_a) * kPitch;
+      float* prow_b = prow_a + kPitch;
       if (valid) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {  // bin l + 8 m = chunk m, position l
-          const uint16_t ha = bf16_bits(pa[m]), hb = bf16_bits(pb[m]);
-          *reinterpret_cast<uint16_t*>(hi_a + m * (kTcM * 16)) = ha;
-          *reinterpret_cast<uint16_t*>(hi_a + m * (kTcM * 16) + 16) = hb;
-          *reinterpret_cast<uint16_t*>(lo_a + m * (kTcM * 16)) = bf16_bits(pa[m] - bf16_value(ha));
-          *reinterpret_cast<uint16_t*>(lo_a + m * (kTcM * 16) + 16) = bf16_bits(pb[m] - bf16_value(hb));
+        for (int m = 0; m < 16; ++m) {
+          prow_a[l + G * m] = pa[m];
+          prow_b[l + G * m] = pb[m];
         }
-        if (l == 0) {  // bin 128 = chunk 16, position 0
-          const uint16_t ha = bf16_bits(pa[16]), hb = bf16_bits(pb[16]);
-          *reinterpret_cast<uint16_t*>(hi_a + 16 * (kTcM * 16)) = ha;
-          *reinterpret_cast<uint16_t*>(hi_a + 16 * (kTcM * 16) + 16) = hb;
-          *reinterpret_cast<uint16_t*>(lo_a + 16 * (kTcM * 16)) = bf16_bits(pa[16] - bf16_value(ha));
-          *reinterpret_cast<uint16_t*>(lo_a + 16 * (kTcM * 16) + 16) = bf16_bits(pb[16] - bf16_value(hb));
+        if (l == 0) {
+          prow_a[Ge::kNfft / 2] = pa[16];
+          prow_b[Ge::kNfft / 2] = pb[16];
         }
       }
       if (l == 0) {
         const int64_t ta = cur.ub * Ge::kFrames + 2 * gi;
         const int64_t oa = (cur.row * p.frames + ta) * (int64_t)width;
-        s_slot[b * kSlots + row_a] = (valid && ta < p.frames) ? oa : -1;
-        s_slot[b * kSlots + row_a + 1] = (valid && ta + 1 < p.frames) ? oa + width : -1;
+        s_slot[b * kRows + slot_a] = (valid && ta < p.frames) ? oa : -1;
+        s_slot[b * kRows + slot_a + 1] = (valid && ta + 1 < p.frames) ? oa + width : -1;
         const int64_t g = cur.row / p.rows_per_group;
-        s_grp[b * kSlots + row_a] = g;
-        s_grp[b * kSlots + row_a + 1] = g;
+        s_grp[b * kRows + slot_a] = g;
+        s_grp[b * kRows + slot_a + 1] = g;
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my plane writes -> async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(s_full + b);
     }
   } else {
-    // =============================== contraction warps =========================================
-    reg_dealloc<kMelRegs>();
-    const int mw = warp - kWarps;  // TMEM lane quadrant == warp % 4
-    if (mw == 0) tmem_alloc(s_tmem, 128);
+    // ============ operand warps (all four), MMA issue (warp 11), epilogue (the first kEpi of them) ============
+    reg_dealloc<kTcEpiRegs>();  // one setmaxnreg for the whole warpgroup
+    const int cw = warp - kWarps;  // == TMEM lane quadrant (warp % 4)
+    const uint32_t acc_cols = 2 * n_pad;  // one accumulator; two of them alternate
+    const uint32_t tmem_cols = acc_cols <= 16 ? 32u : (acc_cols <= 32 ? 64u : (acc_cols <= 64 ? 128u : (acc_cols <= 128 ? 256u : 512u)));
+    if (cw == 0) tmem_alloc(s_tmem, tmem_cols);
     tc_fence_before();
     asm volatile("bar.sync 1, %0;" ::"n"(kMelWarps * 32) : "memory");
     tc_fence_after();
     const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(s_tmem);
     GroupMax gmax{p.stage == B200A_STAGE_FEAT ? p.group_max : nullptr, -1, -CUDART_INF_F};
-    const uint32_t idesc = umma_idesc_bf16(kTcM, n_pad);
-    const uint32_t b_hi_addr = smem_u32(s_b), b_lo_addr = b_hi_addr + plane_b;
-    const uint32_t b_lbo = (uint32_t)n_pad * 16;
-    int it = 0;
-    for (int64_t base = u0; base < p.total_units; base += stride, ++it) {
-      const int b = it & 1;
-      mbar_wait(s_full + b, (it >> 1) & 1);
-      tc_fence_after();
-      if (mw == 0 && lane == 0) {
-        const uint32_t a_hi_addr = smem_u32(s_a + (size_t)b * 2 * kTcPlaneA), a_lo_addr = a_hi_addr + kTcPlaneA;
-#pragma unroll 1
-        for (int s = 0; s < kTcChunks / 2; ++s) {  // K = 16 per MMA = two 16-byte chunks
-          const uint64_t ah = umma_smem_desc(a_hi_addr + s * 2 * kTcM * 16, kTcM * 16, 128);
-          const uint64_t al = umma_smem_desc(a_lo_addr + s * 2 * kTcM * 16, kTcM * 16, 128);
-          const uint64_t bh = umma_smem_desc(b_hi_addr + s * 2 * b_lbo, b_lbo, 128);
-          const uint64_t bl = umma_smem_desc(b_lo_addr + s * 2 * b_lbo, b_lbo, 128);
-          umma_bf16(tmem_d, ah, bh, idesc, s > 0 ? 1u : 0u);
-          umma_bf16(tmem_d, al, bh, idesc, 1u);
-          umma_bf16(tmem_d, ah, bl, idesc, 1u);
-        }
-        umma_commit(s_mma);
-      }
-      mbar_wait(s_mma, it & 1);  // accumulator complete, operand planes of buffer b no longer read
-      tc_fence_after();
-      // epilogue: thread i < 16 of quadrant mw owns tile row 16 mw + i == TMEM lane 32 mw + i
-      const int row = 16 * mw + (lane & 15);
-      const int64_t o = s_slot[b * kSlots + row];
-      const int64_t g = s_grp[b * kSlots + row];
+    // conversion items: (chunk, row) with the row fastest, 128 per round over the four warps
+    constexpr int kItems = (Tc::kChunks - 1) * kRows, kRounds = (kItems + 127) / 128;
+    const int erow = 16 * cw + (lane & 15);  // epilogue: thread i < 16 owns tile row 16 cw + i == TMEM lane 32 cw + i
+
+    // accumulator of tile `t` -> dB / log -> global; o / g: output offset and top_db group of this thread's row
+    auto epilogue = [&](int t, int64_t o, int64_t g) {
+      const uint32_t acc = tmem_d + ((uint32_t)(32 * cw) << 16) + (uint32_t)(t & 1) * acc_cols;
       const bool row_ok = lane < 16 && o >= 0;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty + b);
 #pragma unroll 1
-      for (int c0 = 0; c0 < n_pad; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_d + ((uint32_t)(32 * mw) << 16) + (uint32_t)c0, v);
+      for (int f0 = 0; f0 < n_pad; f0 += 16) {
+        float u[16], w[16], v[16];
+        tmem_ld16(acc + 2 * f0, u);
+        tmem_ld16(acc + 2 * f0 + 16, w);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[q] = u[q] + u[q + 8];
+          v[q + 8] = w[q] + w[q + 8];
+        }
         if (p.stage == B200A_STAGE_FEAT) {
           float mx = -CUDART_INF_F;
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
             v[q] = p.log_mels ? logf(v[q] + 1e-6f) : p.db_mult * log10f(fmaxf(v[q], p.db_amin)) - p.db_offset;
-            if (c0 + q < p.n_mels) mx = fmaxf(mx, v[q]);
+            if (f0 + q < p.n_mels) mx = fmaxf(mx, v[q]);
           }
           gmax.add(g, mx, row_ok);
         }
         if (row_ok) {
-          float* dst = p.out + o + c0;
-          if ((width & 3) == 0 && c0 + 16 <= p.n_mels) {
+          float* dst = p.out + o + f0;
+          if ((width & 3) == 0 && f0 + 16 <= p.n_mels) {
 #pragma unroll
-            for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+            for (int q = 0; q < 16; q += 4)
+              *reinterpret_cast<float4*>(dst + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
           } else {
 #pragma unroll
             for (int q = 0; q < 16; ++q)
-              if (c0 + q < p.n_mels) dst[q] = v[q];
+              if (f0 + q < p.n_mels) dst[q] = v[q];
           }
         }
       }
-      tc_fence_before();  // my tcgen05.ld are done before the next tile's MMAs overwrite the accumulator
-      asm volatile("bar.sync 1, %0;" ::"n"(kMelWarps * 32) : "memory");
+      tc_fence_before();  // my tcgen05.ld are done before this accumulator is handed back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_tfree + (t & 1));
+    };
+
+    int it = 0;
+    int64_t o_prev = -1, g_prev = -1;
+    for (int64_t base = u0; base < p.total_units; base += stride, ++it) {
+      const int b = it & 1;
+      mbar_wait_relaxed(s_full + b, (it >> 1) & 1);
+      int64_t o_cur = -1, g_cur = -1;
+      if (cw < kEpi) {
+        o_cur = s_slot[b * kRows + erow];
+        g_cur = s_grp[b * kRows + erow];
+      }
+      if (it > 0) mbar_wait_relaxed(s_mma, (it - 1) & 1);  // the previous tile's MMAs no longer read the planes
+      {
+        const float* pw = s_pow + (size_t)b * kRows * kPitch;
+#pragma unroll 2
+        for (int rd = 0; rd < kRounds; ++rd) {
+          const int item = rd * 128 + cw * 32 + lane;
+          if (item < kItems) {
+            const int chunk = item / kRows, row = item % kRows;
+            const float4 v0 = *reinterpret_cast<const float4*>(pw + row * kPitch + 8 * chunk);
+            const float4 v1 = *reinterpret_cast<const float4*>(pw + row * kPitch + 8 * chunk + 4);
+            uint4 hi, lo;
+            split_bf16x2(v0.x, v0.y, hi.x, lo.x);
+            split_bf16x2(v0.z, v0.w, hi.y, lo.y);
+            split_bf16x2(v1.x, v1.y, hi.z, lo.z);
+            split_bf16x2(v1.z, v1.w, hi.w, lo.w);
+            unsigned char* dst = s_a + (size_t)item * 16;  // chunk * kRows * 16 + row * 16
+            *reinterpret_cast<uint4*>(dst) = hi;
+            *reinterpret_cast<uint4*>(dst + kPlane) = lo;
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my plane writes -> async proxy
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(s_empty + b);
+        mbar_arrive(s_ready);
+      }
+      if (cw == kMelWarps - 1) {
+        // ---- issue: D[t & 1][:, 2 n0 : 2 n0 + 2 N] += P_hi [F_hi | F_lo] + P_lo [F_hi | F_lo] per k-step ----
+        mbar_wait(s_ready, it & 1);
+        if (it >= 2) mbar_wait(s_tfree + b, ((it >> 1) & 1) ^ 1);  // tile it - 2 has been read out of this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_d + (uint32_t)b * acc_cols;
+#pragma unroll 3
+        for (int s = 0; s < n_steps; ++s) {
+          const TcIssue e = s_issue[s];
+          if (elect_one()) {
+            umma_bf16(acc + e.col, e.a_hi, e.b, e.idesc, s > 0 ? 1u : 0u);  // step 0 spans every column: it clears D
+            umma_bf16(acc + e.col, e.a_lo, e.b, e.idesc, 1u);
+          }
+        }
+        if (elect_one()) umma_commit(s_mma);
+        __syncwarp();
+      }
+      if (cw < kEpi && it > 0) {  // the previous tile's accumulator, while the tensor core works on this one
+        tc_fence_after();
+        epilogue(it - 1, o_prev, g_prev);
+      }
+      o_prev = o_cur;
+      g_prev = g_cur;
+    }
+    if (cw < kEpi && it > 0) {
+      mbar_wait(s_mma, (it - 1) & 1);
       tc_fence_after();
+      epilogue(it - 1, o_prev, g_prev);
     }
     gmax.flush();
-    if (mw == 0) tmem_dealloc(tmem_d, 128);
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"n"(kMelWarps * 32) : "memory");  // every tcgen05.ld is done
+    if (cw == 0) tmem_dealloc(tmem_d, tmem_cols);
   }
 }
 
-// filterbank -> bf16 hi / lo UMMA B planes: B[n][k] = fb[k][n], K-major un-swizzled, n_pad rows, 144 columns
-__global__ void prepare_tc_b_kernel(const float* __restrict__ fb, int n_bins, int n_mels, int n_pad,
-                                    unsigned char* planes) {
-  const int plane = kTcChunks * n_pad * 16;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad * kTcChunks * 8; i += gridDim.x * blockDim.x) {
-    const int n = i / (kTcChunks * 8), k = i - n * (kTcChunks * 8);
-    const float v = (n < n_mels && k < n_bins) ? fb[(size_t)k * n_mels + n] : 0.f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(h));
-    const size_t off = (size_t)(k >> 3) * n_pad * 16 + (size_t)n * 16 + (size_t)(k & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(planes + off) = h;
-    *reinterpret_cast<__nv_bfloat16*>(planes + plane + off) = lo;
+// Banded bf16 hi / lo UMMA B blocks and their step table.  One block.
+__global__ void prepare_tc_kernel(const float* __restrict__ fb, int n_bins, int n_mels, int n_fft, int budget,
+                                  TcPlan* plan, unsigned char* blocks) {
+  __shared__ int s_lo[kTcMaxSteps], s_hi[kTcMaxSteps];
+  __shared__ TcPlan s_plan;
+  const int k_steps = (n_fft / 16 + 2) / 2;  // (2 G + 2) / 2
+  const int n_pad = (n_mels + 15) / 16 * 16;
+  if ((int)threadIdx.x < k_steps) {
+    int lo = n_mels, hi = -1;
+    for (int k = 16 * threadIdx.x; k < 16 * (int)threadIdx.x + 16 && k < n_bins; ++k)
+      for (int n = 0; n < n_mels; ++n)
+        if (fb[(size_t)k * n_mels + n] != 0.f) {
+          lo = min(lo, n);
+          hi = max(hi, n);
+        }
+    s_lo[threadIdx.x] = lo;
+    s_hi[threadIdx.x] = hi;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int steps = 0, off = 0;
+    for (int s = 0; s < k_steps; ++s) {
+      int n0, n;
+      if (s == 0) {  // the first MMA clears the accumulator: every column
+        n0 = 0;
+        n = n_pad;
+      } else if (s_hi[s] < 0) {
+        continue;
+      } else {
+        n0 = s_lo[s] / 8 * 8;
+        n = (s_hi[s] + 1 - n0 + 7) / 8 * 8;
+      }
+      s_plan.step[steps] = TcStep{(uint32_t)off, (uint32_t)n, (uint32_t)n0, (uint32_t)s};
+      off += n * 64;
+      ++steps;
+    }
+    s_plan.steps = steps;
+    s_plan.n_pad = n_pad;
+    s_plan.b_bytes = off;
+    s_plan.ok = (off <= budget && off <= kTcWsBBytes && n_pad <= kTcMaxN) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_plan.ok) {
+    for (int s = 0; s < s_plan.steps; ++s) {
+      const TcStep st = s_plan.step[s];
+      for (int i = threadIdx.x; i < (int)st.n * 16; i += blockDim.x) {
+        const int nl = i >> 4, kk = i & 15;
+        const int n = (int)st.col + nl, k = 16 * (int)st.kstep + kk;
+        const float v = (n < n_mels && k < n_bins) ? fb[(size_t)k * n_mels + n] : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(h));
+        // operand row of filter nl: 16 (nl / 8) + nl % 8 for F_hi, + 8 for F_lo; 2 n rows x 16 B per k chunk
+        const size_t row = (size_t)(nl >> 3) * 16 + (nl & 7);
+        const size_t o = st.b_off + (size_t)(kk >> 3) * st.n * 32 + row * 16 + (size_t)(kk & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(blocks + o) = h;
+        *reinterpret_cast<__nv_bfloat16*>(blocks + o + 128) = lo;
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < (int)(sizeof(TcPlan) / sizeof(int)); i += blockDim.x)
+    reinterpret_cast<int*>(plan)[i] = reinterpret_cast<const int*>(&s_plan)[i];
+}
+
+// The mel / MFCC-feature kernel: tcgen05 contraction when the prepared plan says the banded filterbank fits
+// shared memory (every real mel / linear filterbank does), mma.sync contraction otherwise.
+template <int POWER_MODE, int G, int HG>
+__global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft_pow2_mel_kernel(const Pow2Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (p.tc != nullptr && p.tc->ok)
+    mel_body_tc<POWER_MODE, G, HG>(p, smem_raw);
+  else
+    mel_body_mma<POWER_MODE, G, HG>(p, smem_raw);
 }
 
 // ---- table preparation ------------------------------------------------------------------------
@@ -1259,14 +1443,13 @@ static_assert(kMaxItemsPerWarp * kMelWarps >= kMaxItems,
 
 }  // namespace
 
-// n_fft = 256 mel stages run their contraction on tcgen05 unless B200A_TC256=0 asks for the mma.sync path
-static int tc_n_pad(int n_mels) { return (n_mels + 15) / 16 * 16; }
-static bool tc256_applicable(const b200a_frontend_desc& d) {
+// mel stages of n_fft <= 1024 run their contraction on tcgen05 unless B200A_TC=0 asks for the mma.sync path
+static bool tc_enabled(const b200a_frontend_desc& d) {
   static const bool enabled = [] {
-    const char* e = std::getenv("B200A_TC256");
+    const char* e = std::getenv("B200A_TC");
     return !(e && e[0] == '0');
   }();
-  return enabled && d.n_fft == 256 && d.onesided && d.n_mels > 0 && tc_n_pad(d.n_mels) <= kTcMaxN;
+  return enabled && d.n_fft <= 1024 && d.onesided && d.n_mels > 0 && d.n_mels <= kTcMaxN;
 }
 
 size_t pow2_workspace_extra(const b200a_frontend_desc* d) {
@@ -1290,10 +1473,10 @@ int pow2_prepare(const b200a_frontend_desc* d, void* ws, size_t ws_bytes, cudaSt
                                               mel_tiles(d->n_mels), reinterpret_cast<MelPlan*>(base + e.plan),
                                               reinterpret_cast<float4*>(base + e.frags));
   }
-  if (tc256_applicable(*d)) {
-    const int n_pad = tc_n_pad(d->n_mels);
-    prepare_tc_b_kernel<<<(n_pad * kTcChunks * 8 + 255) / 256, 256, 0, stream>>>(
-        reinterpret_cast<const float*>(base + l.fb), d->n_fft / 2 + 1, d->n_mels, n_pad, base + e.tc_b);
+  if (tc_enabled(*d)) {
+    prepare_tc_kernel<<<1, 256, 0, stream>>>(reinterpret_cast<const float*>(base + l.fb), d->n_fft / 2 + 1, d->n_mels,
+                                             d->n_fft, tc_b_budget(d->n_fft), reinterpret_cast<TcPlan*>(base + e.tc_plan),
+                                             base + e.tc_b);
   }
   return launch_status();
 }
@@ -1310,10 +1493,10 @@ static int num_sms() {
 }
 
 // persistent: one resident CTA per SM, units dealt round-robin (every CTA gets the same count +-1)
-static int64_t persistent_grid(const Pow2Params& p) {
+static int64_t persistent_grid(const Pow2Params& p, int warps = kWarps) {
   const int sms = num_sms();
   if (sms < 0) return -1;
-  const int64_t iters = (p.total_units + kWarps - 1) / kWarps;
+  const int64_t iters = (p.total_units + warps - 1) / warps;
   const int64_t grid = iters < sms ? iters : sms;
   return grid < 1 ? 1 : grid;
 }
@@ -1321,14 +1504,19 @@ static int64_t persistent_grid(const Pow2Params& p) {
 template <int POWER_MODE, int G, int HG>
 static int launch_power(const Pow2Params& p, cudaStream_t stream) {
   using Ge = Geo<G>;
-  const size_t smem = sizeof(float2) * (32 * 32 + kWarps * Ge::kTileF2) + sizeof(float) * kWarps * Ge::kStageFloats +
-                      sizeof(uint64_t) * kWarps;
-  auto kern = stft_pow2_power_kernel<POWER_MODE, G, HG>;
+  // the transform is latency bound: as many warps as shared memory (tile + staging buffer each) and the
+  // register file (168 registers at 12 warps, no spills) allow
+  constexpr int NW = G == 8 ? 10 : 12;
+  const size_t smem = sizeof(float2) * (32 * 32 + NW * Ge::kTileF2) + sizeof(float) * NW * Ge::kStageFloats +
+                      sizeof(uint64_t) * NW;
+  static_assert(sizeof(float2) * (32 * 32 + NW * Ge::kTileF2) + sizeof(float) * NW * Ge::kStageFloats + 8 * NW <= 227 * 1024,
+                "power kernel shared memory");
+  auto kern = stft_pow2_power_kernel<POWER_MODE, G, HG, NW>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return B200A_ECUDA;
-  const int64_t grid = persistent_grid(p);
+  const int64_t grid = persistent_grid(p, NW);
   if (grid < 0) return B200A_ECUDA;
-  kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(p);
+  kern<<<(unsigned)grid, NW * 32, smem, stream>>>(p);
   return launch_status();
 }
 
@@ -1341,29 +1529,13 @@ static int launch_mel(const Pow2Params& p, cudaStream_t stream) {
                       sizeof(int64_t) * 4 * Ge::kSlots + sizeof(uint64_t) * (kWarps + 4) + sizeof(MelPlan) +
                       sizeof(float4) * 32 * kFragSmemSteps;
   if (smem > 227 * 1024) return B200A_EUNSUPPORTED;
+  static_assert(TcGeo<G>::kFixed + TcGeo<G>::kBBudget <= 227 * 1024 && TcGeo<G>::kBBudget >= 24 * 1024, "tcgen05 layout");
   auto kern = stft_pow2_mel_kernel<POWER_MODE, G, HG>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return B200A_ECUDA;
   const int64_t grid = persistent_grid(p);
   if (grid < 0) return B200A_ECUDA;
-  kern<<<(unsigned)grid, (kWarps + kMelWarps) * 32, smem, stream>>>(p);
-  return launch_status();
-}
-
-template <int POWER_MODE>
-static int launch_tc256(const Pow2Params& p, const unsigned char* tc_b, cudaStream_t stream) {
-  using Ge = Geo<kTcG>;
-  const int n_pad = tc_n_pad(p.n_mels);
-  const size_t smem = 4 * (size_t)kTcPlaneA + 2 * (size_t)kTcChunks * n_pad * 16 +
-                      sizeof(float2) * (kWarps * Ge::kTileF2 + 32 * kTcG) + sizeof(int64_t) * 4 * Ge::kSlots +
-                      sizeof(uint64_t) * (kWarps + 5) + 16;
-  if (smem > 227 * 1024) return B200A_EUNSUPPORTED;
-  auto kern = stft256_mel_tc_kernel<POWER_MODE>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-    return B200A_ECUDA;
-  const int64_t grid = persistent_grid(p);
-  if (grid < 0) return B200A_ECUDA;
-  kern<<<(unsigned)grid, (kWarps + kMelWarps) * 32, smem, stream>>>(p, tc_b, n_pad);
+  kern<<<(unsigned)grid, (kWarps + kMelWarps) * 32, p.tc != nullptr ? (size_t)227 * 1024 : smem, stream>>>(p);
   return launch_status();
 }
 
@@ -1431,6 +1603,8 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
   p.plan = reinterpret_cast<const MelPlan*>(base + e.plan);
   p.frags = reinterpret_cast<const float4*>(base + e.frags);
   p.hdr = reinterpret_cast<const WsHeader*>(base + l.header);
+  p.tc = tc_enabled(*d) ? reinterpret_cast<const TcPlan*>(base + e.tc_plan) : nullptr;
+  p.tc_b = base + e.tc_b;
   p.hop = d->hop;
   p.pad = d->pad;
   p.center = d->center;
@@ -1456,8 +1630,6 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
     const float2* tw_eo = reinterpret_cast<const float2*>(base + e.tw_eo);
     return d->power == 2.f ? launch_eo<2>(p, tw_eo, mel, stream) : launch_eo<0>(p, tw_eo, mel, stream);
   }
-  if (mel && tc256_applicable(*d))
-    return d->power == 2.f ? launch_tc256<2>(p, base + e.tc_b, stream) : launch_tc256<0>(p, base + e.tc_b, stream);
   return d->power == 2.f ? launch_any<2>(p, d->n_fft, mel, stream) : launch_any<0>(p, d->n_fft, mel, stream);
 }
 

@@ -299,7 +299,7 @@ def test_config2_full_size_properties():
     z = m(x[:4, 512:])
     assert torch.equal(z[:, :, 2:600], y[:4, :, 4:602])
     z1 = m(x[:4, 256:])  # odd shift: same values up to the pair partner's round-off
-    assert torch.allclose(z1[:, :, 2:600], y[:4, :, 3:601], rtol=1e-5, atol=1e-4)
+    assert torch.allclose(z1[:, :, 2:600], y[:4, :, 3:601], rtol=5e-5, atol=1e-4)  # bf16x3 products: ~2^-16
     # (4) a sample of rows against the fp64 oracle
     exp = O.mel_spectrogram(x[idx].cpu().numpy(), sample_rate=16000, n_fft=1024, hop_length=256, n_mels=80,
                             fb=m.mel_scale.fb.cpu().numpy())
