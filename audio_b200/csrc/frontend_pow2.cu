@@ -11,19 +11,25 @@
 //   pass 2  32/G DFTs of G points over the former lane index, in registers  -> Z[l + G q + 32 k1]
 //   un-pack the two real spectra with one shuffle per needed value:  A = (Z[k] + conj Z[N-k]) / 2,
 //                                                                    B = (Z[k] - conj Z[N-k]) / 2i
-//   every lane ends with bins k = l + G m (m < 16) of its two frames; |.|^p -> global (Spectrogram), or
-//   -> a double-buffered shared power tile of all frames the CTA finished this iteration.
-//   mel     warp specialised: 8 transform warps publish power rows, 4 contraction warps multiply each
-//           finished tile with the filterbank on the tensor pipe: mma.sync m16n8k8 TF32 with
-//           error-compensated operands (P_hi*F_hi + P_lo*F_hi + P_hi*F_lo, ~2^-21 relative), visiting
-//           only the k-steps where a group of 8 filters is non-zero; (-> dB / log) -> global.
+//   every lane ends with bins k = l + G m (m < 16) of its two frames; |.|^p -> global (Spectrogram: 16
+//   independent warps per CTA), or -> shared memory for the mel contraction.
+//   mel     warp specialised, two bodies behind one kernel (picked by the plan prepare_tc_kernel built):
+//           tcgen05 (n_fft <= 1024, banded filterbank fits shared memory: every real mel / linear bank):
+//             12 (n_fft = 256: 8) transform warps publish fp32 power values in UMMA core-matrix order,
+//             4 operand warps convert them in place to bf16 hi / lo planes, one thread issues
+//             tcgen05.mma kind::f16 (M = 64, accumulator in TMEM, banded k-steps), the operand warps read
+//             the previous tile's accumulator with tcgen05.ld; error-compensated bf16, ~2^-16 relative.
+//           mma.sync (any other filterbank up to 512 filters, n_fft = 2048, or B200A_TC=0):
+//             8 transform warps publish power rows, 4 contraction warps multiply each finished tile with
+//             the filterbank: m16n8k8 TF32 with error-compensated operands (P_hi*F_hi + P_lo*F_hi +
+//             P_hi*F_lo, ~2^-21 relative), visiting only the k-steps where a group of 8 filters is non-zero.
+//           (-> dB / log) -> global.
 // Nothing but the waveform is read from HBM and nothing but the final features is written.
 //
-// Why mma.sync and not tcgen05 for the mel contraction: a tcgen05.mma tile needs M >= 64 frames of
-// the A operand resident (64 x 513 power values in two bf16 planes or one fp32 plane = 131 KB, or
-// > 512 TMEM columns) next to the FFT working set of the warps that produce them; that does not fit
-// the 227 KB of shared memory per SM at n_fft = 1024.  The warp-level fragment MMA has M = 16.
-// See DESIGN.md ("mel projection").
+// tcgen05 at n_fft = 1024: an M = 64 tile of 513 bins does not fit next to the transform working set, so
+// the tile has 24 real rows (what 12 warps finish per iteration) and the other 40 operand rows alias
+// whatever follows in shared memory -- each accumulator row depends on its own operand row only, and the
+// TMEM lanes of those rows are never read.  See DESIGN.md ("mel projection").
 //
 // Reference semantics: src/torchaudio/functional/functional.py:54-145 and
 // transforms/_transforms.py:403-415, :701-705 (see frontend_generic.cu for the any-size path).
@@ -446,14 +452,14 @@ __device__ __forceinline__ void load_window(const Pow2Params& p, int lane, float
 // ------------------------------------------------------------------------------------------------
 // Spectrogram kernel: 8 independent warps, power spectra straight to global memory.
 // ------------------------------------------------------------------------------------------------
-template <int POWER_MODE, int G, int HG, int NW>
+template <int POWER_MODE, int G, int HG, int NW, bool STAGE_IS_TILE>
 __global__ void __launch_bounds__(NW * 32, 1) stft_pow2_power_kernel(const Pow2Params p) {
   using Ge = Geo<G>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* s_tw = reinterpret_cast<float2*>(smem_raw);                                    // [32][G]
   float2* s_tile_all = s_tw + 32 * 32;                                                   // [NW][kTileF2]
   float* s_stage_all = reinterpret_cast<float*>(s_tile_all + NW * Ge::kTileF2);      // [NW][kStageFloats]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage_all + NW * Ge::kStageFloats);  // [NW]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage_all + (STAGE_IS_TILE ? 0 : NW * Ge::kStageFloats));  // [NW]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 32 * G; i += blockDim.x) s_tw[i] = p.tw2d[i];
@@ -462,7 +468,7 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_pow2_power_kernel(const Pow2P
   __syncthreads();
 
   float2* tile = s_tile_all + warp * Ge::kTileF2;
-  float* stage = s_stage_all + warp * Ge::kStageFloats;
+  float* stage = STAGE_IS_TILE ? reinterpret_cast<float*>(tile) : s_stage_all + warp * Ge::kStageFloats;
   uint64_t* bar = s_bar + warp;
   float wreg[32];
   load_window<G>(p, lane, wreg);
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_pow2_power_kernel(const Pow2P
   }
   for (; cur.u < p.total_units; cur.advance()) {
     float pa[17], pb[17];
-    transform_unit<POWER_MODE, G, HG, false>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa, pb);
+    transform_unit<POWER_MODE, G, HG, STAGE_IS_TILE>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa, pb);
     const int64_t ta = cur.ub * Ge::kFrames + 2 * gi;
     const bool has_a = ta < p.frames, has_b = ta + 1 < p.frames;
     float* oa = p.out + (cur.row * p.frames + ta) * Ge::kBins;
@@ -571,7 +577,7 @@ __device__ __forceinline__ void contract_tile(const Pow2Params& p, const MelPlan
 // ------------------------------------------------------------------------------------------------
 constexpr int kFftRegs = 200, kMelRegs = 96;  // 256*200 + 128*96 = 63488 <= 64512 = 384 * 168
 
-template <int POWER_MODE, int G, int HG>
+template <int POWER_MODE, int G, int HG, int FFT_REGS>
 __device__ __forceinline__ void mel_body_mma(const Pow2Params& p, unsigned char* smem_raw) {
   using Ge = Geo<G>;
   constexpr int kSlots = Ge::kSlots, kPitch = Ge::kPitch;
@@ -618,7 +624,7 @@ __device__ __forceinline__ void mel_body_mma(const Pow2Params& p, unsigned char*
 
   if (warp < kWarps) {
     // =============================== transform warps ===========================================
-    reg_alloc<kFftRegs>();
+    reg_alloc<FFT_REGS>();
     float2* tile = s_tile_all + warp * Ge::kTileF2;
     float* stage = reinterpret_cast<float*>(tile);
     uint64_t* bar = s_bar + warp;
@@ -669,6 +675,8 @@ __device__ __forceinline__ void mel_body_mma(const Pow2Params& p, unsigned char*
       __syncwarp();
       if (lane == 0) mbar_arrive(s_full + b);
     }
+  } else if (warp >= kWarps + kMelWarps) {
+    reg_dealloc<24>();  // launched for the tcgen05 body's 12 transform warps: hand the registers back and leave
   } else {
     // =============================== contraction warps =========================================
     reg_dealloc<kMelRegs>();
@@ -677,7 +685,7 @@ __device__ __forceinline__ void mel_body_mma(const Pow2Params& p, unsigned char*
     int it = 0;
     for (int64_t base = u0; base < p.total_units; base += stride, ++it) {
       const int b = it & 1;
-      mbar_wait_relaxed(s_full + b, (it >> 1) & 1);
+      mbar_wait(s_full + b, (it >> 1) & 1);
 #pragma unroll 1
       for (int mt = 0; mt < kSlots / 16; ++mt)  // 16-frame MMA tiles of this iteration
         contract_tile<kPitch>(p, s_plan, s_frags, frags_in_smem, mw, lane, s_pow + (size_t)(b * kSlots + 16 * mt) * kPitch,
@@ -976,25 +984,29 @@ __global__ void prepare_tw_eo_kernel(float2* tw_eo) {  // [17][32]: W_2048^(l + 
 // ================================================================================================
 // Mel contraction on tcgen05 (5th-generation tensor cores, accumulator in tensor memory).
 //
-// One CTA iteration finishes R = 16 / 32 / 64 frames (n_fft = 1024 / 512 / 256).  Three roles:
-//   transform warps 0-7   publish fp32 power rows into the double-buffered shared tile (as in the
-//                         mma.sync body) and arrive on the tile's `full` barrier
-//   operand warps 8-11    split every power value into bf16 hi + bf16 lo and write the two K-major,
-//                         un-swizzled UMMA operand planes (8-row x 16-byte core matrices; chunk = 8 bins,
-//                         R rows per chunk), fence them to the async proxy, release the fp32 tile
-//   warp 8                issues, per k-step of 16 bins,
-//                             D[:, n0:n0+N] += P_hi F_hi + P_lo F_hi + P_hi F_lo   (tcgen05.mma kind::f16, M = 64)
-//                         into n_mels TMEM columns and commits to an mbarrier.  The filterbank sits in
-//                         shared memory as BANDED UMMA B blocks: for each k-step only the filters that are
-//                         non-zero there (rounded to groups of 8), bf16 hi + lo.  Tile rows >= R of the
-//                         M = 64 instruction alias whatever follows in shared memory and land in TMEM
-//                         lanes nobody reads (an accumulator row depends on its own operand row only).
-//   epilogue warps        R/16 of the four (one TMEM lane quadrant each) tcgen05.ld their 16 frames,
-//                         apply dB / log, track the top_db maximum and store.
+// Moving the contraction to the tensor core frees the registers and issue slots of four mma.sync warps, so
+// this body runs NW = 12 transform warps (n_fft >= 512; the transform is latency bound and scales with
+// resident warps) next to four light "operand" warps.  One CTA iteration finishes R = 2 NW (32 / G) frames.
+//   transform warps     publish fp32 power values into the OPERAND BUFFER, already in the tensor core's
+//                       K-major core-matrix order: chunk = 8 bins; per chunk, per group of 8 frames, a
+//                       256-byte block [8 rows x 8 floats]; arrive on `full`
+//   operand warps       convert each block IN PLACE to [8 rows x 8 bf16 hi | 8 rows x 8 bf16 lo] (read 32 B,
+//                       __syncwarp, write 16 + 16 B), fence to the async proxy, arrive on `ready`
+//   warp NW + 3         issues, per k-step of 16 bins,
+//                           D[:, 2 n0 : 2 n0 + 2 N] += P_hi [F_hi | F_lo] + P_lo [F_hi | F_lo]   (tcgen05.mma kind::f16,
+//                       M = 64, two instructions) and commits to the buffer's `mma` barrier, which is also what
+//                       the transform warps wait on before they publish into that buffer again.  The filterbank
+//                       sits in shared memory as BANDED UMMA B blocks: for each k-step only the filters that
+//                       are non-zero there (groups of 8: 8 rows F_hi, 8 rows F_lo), so filter f owns accumulator
+//                       columns 16 (f / 8) + f % 8 and + 8.  Tile rows >= R of the M = 64 instruction alias
+//                       whatever follows in shared memory and land in TMEM lanes nobody reads (an accumulator
+//                       row depends on its own operand row only).
+//   epilogue            ceil(R / 16) of the operand warps (one TMEM lane quadrant each) tcgen05.ld the PREVIOUS
+//                       tile's accumulator (two accumulators alternate) while the tensor core works on the
+//                       current one: hi + lo columns, dB / log, top_db maximum, store.
 // Error-compensated bf16 carries ~2^-16 relative error per product (the 1e-4 bar; the TF32x3 mma.sync body
-// ~2^-21); the contraction costs the SM ~1.5 k issue slots per tile instead of ~4.4 k.
+// ~2^-21).
 // ================================================================================================
-constexpr int kTcFftRegs = 216, kTcEpiRegs = 72;  // 256*216 + 128*72 = 64512 = 384 * 168
 constexpr int kTcMaxSteps = 34;       // k-steps of 16 bins (n_fft = 1024: 33)
 constexpr int kTcMaxN = 128;          // filters: 2 accumulator columns each, two accumulators in 512 TMEM columns
 constexpr int kTcWsBBytes = 96 * 1024;  // workspace reserved for the banded B blocks
@@ -1002,14 +1014,14 @@ constexpr int kTcWsBBytes = 96 * 1024;  // workspace reserved for the banded B b
 struct TcStep {
   uint32_t b_off;  // byte offset of the step's block in the B region (64 n bytes: 2 k-chunks x 2 n operand rows)
   uint32_t n;      // filters covered (multiple of 8)
-  uint32_t col;    // first accumulator column == first filter
+  uint32_t col;    // first filter
   uint32_t kstep;  // which 16 bins: [16 kstep, 16 kstep + 16)
 };
 struct TcPlan {  // built on the device by prepare_tc_kernel
   int ok, steps, n_pad, b_bytes;
   TcStep step[kTcMaxSteps];
 };
-struct __align__(16) TcIssue {  // ready-to-issue descriptors of one k-step, built per CTA
+struct __align__(16) TcIssue {  // ready-to-issue descriptors of one k-step (operand buffer 0), built per CTA
   uint64_t a_hi, a_lo, b;
   uint32_t idesc, col;
 };
@@ -1017,17 +1029,21 @@ struct __align__(16) TcIssue {  // ready-to-issue descriptors of one k-step, bui
 template <int G>
 struct TcGeo {
   using Ge = Geo<G>;
-  static constexpr int kRows = Ge::kSlots;                 // real frames per tile
+  static constexpr int NW = G == 8 ? 8 : 12;               // transform warps
+  static constexpr int NB = G == 8 ? 2 : 1;                // operand buffers
+  static constexpr int kThreads = (NW + kMelWarps) * 32;
+  static constexpr int kFftRegs = NW == 12 ? 144 : 216;    // 384*144 + 128*80 = 65536 = 512*128; 256*216 + 128*72 = 64512
+  static constexpr int kOpRegs = NW == 12 ? 80 : 72;
+  static constexpr int kRows = NW * Ge::kFrames;           // frames per tile: 24 / 48 / 64
   static constexpr int kChunks = 2 * G + 2;                // ceil((16 G + 1) / 8) rounded up to even
   static constexpr int kSteps = kChunks / 2;
-  static constexpr int kPlane = kChunks * kRows * 16;      // bytes of one operand plane
-  static constexpr int kEpi = kRows / 16;                  // epilogue warps == TMEM lane quadrants in use
-  static constexpr int kPowBytes = 2 * kRows * Ge::kPitch * 4;
-  static constexpr int kFixed = 2 * kPlane + kPowBytes + 8 * (kWarps * Ge::kTileF2 + 32 * G) + 32 * kRows +
-                                (int)sizeof(TcIssue) * kTcMaxSteps + 8 * (kWarps + 8) + 16;
+  static constexpr int kChunkStride = kRows * 32 + 32;     // bytes; == 32 (mod 128): conflict-free publishing
+  static constexpr int kOperand = kChunks * kChunkStride;  // bytes of one operand buffer
+  static constexpr int kEpi = (kRows + 15) / 16;           // epilogue warps == TMEM lane quadrants in use
+  static constexpr int kFixed = NB * kOperand + 8 * (NW * Ge::kTileF2 + 32 * G) + 16 * NB * kRows +
+                                (int)sizeof(TcIssue) * kTcMaxSteps + 8 * (NW + 4 * NB + 4) + 16;
   static constexpr int kBBudget = ((227 * 1024 - kFixed) / 128) * 128;
-  static_assert(kSteps <= kTcMaxSteps && kRows <= 64, "one M = 64 tile per iteration");
-  static_assert(Ge::kPitch >= 8 * (kChunks - 1), "the last real chunk reads 8 floats of a power row");
+  static_assert(kSteps <= kTcMaxSteps && kRows <= 64 && kRows % 8 == 0, "one M = 64 tile per iteration");
 };
 inline int tc_b_budget(int n_fft) {
   return n_fft == 1024 ? TcGeo<32>::kBBudget : (n_fft == 512 ? TcGeo<16>::kBBudget : TcGeo<8>::kBBudget);
@@ -1049,73 +1065,65 @@ template <int POWER_MODE, int G, int HG>
 __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* smem_raw) {
   using Ge = Geo<G>;
   using Tc = TcGeo<G>;
-  constexpr int kRows = Tc::kRows, kPlane = Tc::kPlane, kEpi = Tc::kEpi, kPitch = Ge::kPitch;
-  unsigned char* s_a = smem_raw;                                                   // [hi | lo] operand planes
-  unsigned char* s_b = s_a + 2 * kPlane;                                           // banded B blocks
-  float* s_pow = reinterpret_cast<float*>(s_b + Tc::kBBudget);                     // [2][kRows][kPitch]
-  float2* s_tile_all = reinterpret_cast<float2*>(s_pow + 2 * kRows * kPitch);      // [kWarps][kTileF2]
-  float2* s_tw = s_tile_all + kWarps * Ge::kTileF2;                                // [32][G]
-  int64_t* s_slot = reinterpret_cast<int64_t*>(s_tw + 32 * G);                     // [2][kRows]
-  int64_t* s_grp = s_slot + 2 * kRows;                                             // [2][kRows]
-  TcIssue* s_issue = reinterpret_cast<TcIssue*>(s_grp + 2 * kRows);                // [kTcMaxSteps]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_issue + kTcMaxSteps);            // [kWarps] staging
-  uint64_t* s_full = s_bar + kWarps;                                               // [2] fp32 tile published
-  uint64_t* s_empty = s_full + 2;                                                  // [2] fp32 tile converted
-  uint64_t* s_ready = s_empty + 2;                                                 // [1] operand planes written
-  uint64_t* s_mma = s_ready + 1;                                                   // [1] accumulator complete
-  uint64_t* s_tfree = s_mma + 1;                                                   // [2] accumulator read out
+  constexpr int NW = Tc::NW, NB = Tc::NB, kRows = Tc::kRows, kEpi = Tc::kEpi, kStride = Tc::kChunkStride;
+  unsigned char* s_a = smem_raw;                                                   // [NB] operand buffers
+  unsigned char* s_b = s_a + NB * Tc::kOperand;                                    // banded B blocks
+  float2* s_tile_all = reinterpret_cast<float2*>(s_b + Tc::kBBudget);              // [NW][kTileF2]
+  float2* s_tw = s_tile_all + NW * Ge::kTileF2;                                    // [32][G]
+  int64_t* s_slot = reinterpret_cast<int64_t*>(s_tw + 32 * G);                     // [NB][kRows]
+  int64_t* s_grp = s_slot + NB * kRows;                                            // [NB][kRows]
+  TcIssue* s_issue = reinterpret_cast<TcIssue*>(s_grp + NB * kRows);               // [kTcMaxSteps]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_issue + kTcMaxSteps);            // [NW] staging
+  uint64_t* s_full = s_bar + NW;                                                   // [NB] fp32 values published
+  uint64_t* s_ready = s_full + NB;                                                 // [NB] converted to bf16 planes
+  uint64_t* s_mma = s_ready + NB;                                                  // [NB] MMAs of the buffer complete
+  uint64_t* s_tfree = s_mma + NB;                                                  // [2] accumulator read out
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_tfree + 2);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const int n_steps = p.tc->steps, n_pad = p.tc->n_pad;
   for (int i = tid; i < 32 * G; i += blockDim.x) s_tw[i] = p.tw2d[i];
-  {  // operand planes start as zeros (the chunk beyond n_fft/2 stays zero), B blocks come prepared
+  {  // the pad chunk of every operand buffer stays zero; B blocks come prepared
     uint4* a4 = reinterpret_cast<uint4*>(s_a);
-    for (int i = tid; i < 2 * kPlane / 16; i += blockDim.x) a4[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < NB * Tc::kOperand / 16; i += blockDim.x) a4[i] = make_uint4(0, 0, 0, 0);
     const uint4* src = reinterpret_cast<const uint4*>(p.tc_b);
     uint4* b4 = reinterpret_cast<uint4*>(s_b);
     const int n16 = p.tc->b_bytes / 16;
     for (int i = tid; i < n16; i += blockDim.x) b4[i] = src[i];
   }
-  // columns >= n_bins of every power row are read by the last chunk: keep them zero
-  for (int i = tid; i < 2 * kRows * (kPitch - Ge::kBins); i += blockDim.x) {
-    const int r = i / (kPitch - Ge::kBins), c = i - r * (kPitch - Ge::kBins);
-    s_pow[r * kPitch + Ge::kBins + c] = 0.f;
-  }
   if (tid < n_steps) {
     const TcStep st = p.tc->step[tid];
-    const uint32_t hi = smem_u32(s_b) + st.b_off, a_addr = smem_u32(s_a) + st.kstep * 2 * kRows * 16;
+    const uint32_t a_addr = smem_u32(s_a) + st.kstep * 2 * kStride;
     TcIssue o;
-    o.a_hi = umma_smem_desc(a_addr, kRows * 16, 128);
-    o.a_lo = umma_smem_desc(a_addr + kPlane, kRows * 16, 128);
-    o.b = umma_smem_desc(hi, st.n * 32, 128);      // 2 n operand rows: per 8 filters, 8 hi rows then 8 lo rows
+    o.a_hi = umma_smem_desc(a_addr, kStride, 256);        // 8-row groups 256 B apart: [hi 128 B | lo 128 B]
+    o.a_lo = umma_smem_desc(a_addr + 128, kStride, 256);
+    o.b = umma_smem_desc(smem_u32(s_b) + st.b_off, st.n * 32, 128);  // 2 n rows: per 8 filters, 8 hi rows then 8 lo rows
     o.idesc = umma_idesc_bf16(64, 2 * (int)st.n);
-    o.col = 2 * st.col;                            // filter f: columns 16 (f / 8) + f % 8 (x F_hi) and + 8 (x F_lo)
+    o.col = 2 * st.col;
     s_issue[tid] = o;
   }
-  if (tid < kWarps) mbar_init(s_bar + tid, 1);
+  if (tid < NW) mbar_init(s_bar + tid, 1);
   if (tid == 0) {
-    mbar_init(s_full + 0, kWarps);
-    mbar_init(s_full + 1, kWarps);
-    mbar_init(s_empty + 0, kMelWarps);
-    mbar_init(s_empty + 1, kMelWarps);
-    mbar_init(s_ready, kMelWarps);
-    mbar_init(s_mma, 1);
+    for (int i = 0; i < NB; ++i) {
+      mbar_init(s_full + i, NW);
+      mbar_init(s_ready + i, kMelWarps);
+      mbar_init(s_mma + i, 1);
+    }
     mbar_init(s_tfree + 0, kEpi);
     mbar_init(s_tfree + 1, kEpi);
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // B blocks, zeroed planes -> the tensor core
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // B blocks, zeroed buffers -> the tensor core
   __syncthreads();
 
-  const int64_t stride = (int64_t)gridDim.x * kWarps;
-  const int64_t u0 = (int64_t)blockIdx.x * kWarps;
+  const int64_t stride = (int64_t)gridDim.x * NW;
+  const int64_t u0 = (int64_t)blockIdx.x * NW;
   const int width = p.n_mels;
 
-  if (warp < kWarps) {
+  if (warp < NW) {
     // =============================== transform warps ===========================================
-    reg_alloc<kTcFftRegs>();
+    reg_alloc<Tc::kFftRegs>();
     float2* tile = s_tile_all + warp * Ge::kTileF2;
     float* stage = reinterpret_cast<float*>(tile);
     uint64_t* bar = s_bar + warp;
@@ -1131,6 +1139,10 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
       if (lane == 0) issue_bulk<G>(p, half, cur.row, cur.ub, stage, bar);
       staged = true;
     }
+    // value (row, bin k) lives at chunk (k / 8), 8-row group (row / 8): [row % 8][k % 8] floats
+    const int row_a = Ge::kFrames * warp + 2 * gi;  // even: rows a and a + 1 share the 8-row group
+    const int lane_off = (l >> 3) * kStride + (row_a >> 3) * 256 + (row_a & 7) * 32 + (l & 7) * 4;
+    constexpr int kStepM = (G / 8) * kStride;
     int it = 0;
     for (int64_t base = u0; base < p.total_units; base += stride, ++it, cur.advance()) {
       const bool valid = cur.u < p.total_units;
@@ -1138,47 +1150,50 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
       if (valid)
         transform_unit<POWER_MODE, G, HG, true>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
                                                 pb);
-      const int b = it & 1;
-      if (it >= 2) mbar_wait(s_empty + b, ((it >> 1) & 1) ^ 1);  // the operand warps have converted this buffer
-      const int slot_a = Ge::kFrames * warp + 2 * gi;
-      float* prow_a = s_pow + (size_t)(b * kRows + slot_a) * kPitch;
-      float* prow_b = prow_a + kPitch;
+      const int b = it % NB;
+      if (it >= NB) mbar_wait(s_mma + b, ((it / NB) & 1) ^ 1);  // the tensor core has consumed this buffer
+      unsigned char* dst = s_a + (size_t)b * Tc::kOperand + lane_off;
       if (valid) {
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
-          prow_a[l + G * m] = pa[m];
-          prow_b[l + G * m] = pb[m];
+          *reinterpret_cast<float*>(dst + m * kStepM) = pa[m];
+          *reinterpret_cast<float*>(dst + m * kStepM + 32) = pb[m];
         }
-        if (l == 0) {
-          prow_a[Ge::kNfft / 2] = pa[16];
-          prow_b[Ge::kNfft / 2] = pb[16];
+        if (l == 0) {  // bin n_fft/2 opens chunk 2 G: write the whole 8-float row, the other 7 are zeros
+          float4* ra = reinterpret_cast<float4*>(dst + 16 * kStepM);
+          ra[0] = make_float4(pa[16], 0.f, 0.f, 0.f);
+          ra[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          ra[2] = make_float4(pb[16], 0.f, 0.f, 0.f);
+          ra[3] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       if (l == 0) {
         const int64_t ta = cur.ub * Ge::kFrames + 2 * gi;
         const int64_t oa = (cur.row * p.frames + ta) * (int64_t)width;
-        s_slot[b * kRows + slot_a] = (valid && ta < p.frames) ? oa : -1;
-        s_slot[b * kRows + slot_a + 1] = (valid && ta + 1 < p.frames) ? oa + width : -1;
+        s_slot[b * kRows + row_a] = (valid && ta < p.frames) ? oa : -1;
+        s_slot[b * kRows + row_a + 1] = (valid && ta + 1 < p.frames) ? oa + width : -1;
         const int64_t g = cur.row / p.rows_per_group;
-        s_grp[b * kRows + slot_a] = g;
-        s_grp[b * kRows + slot_a + 1] = g;
+        s_grp[b * kRows + row_a] = g;
+        s_grp[b * kRows + row_a + 1] = g;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(s_full + b);
     }
   } else {
-    // ============ operand warps (all four), MMA issue (warp 11), epilogue (the first kEpi of them) ============
-    reg_dealloc<kTcEpiRegs>();  // one setmaxnreg for the whole warpgroup
-    const int cw = warp - kWarps;  // == TMEM lane quadrant (warp % 4)
+    // ============ operand warps (all four), MMA issue (the last), epilogue (the first kEpi of them) ============
+    reg_dealloc<Tc::kOpRegs>();  // one setmaxnreg for the whole warpgroup
+    const int cw = warp - NW;    // == TMEM lane quadrant (NW % 4 == 0)
+    static_assert(NW % 4 == 0, "operand warp i must own TMEM lane quadrant i");
     const uint32_t acc_cols = 2 * n_pad;  // one accumulator; two of them alternate
-    const uint32_t tmem_cols = acc_cols <= 16 ? 32u : (acc_cols <= 32 ? 64u : (acc_cols <= 64 ? 128u : (acc_cols <= 128 ? 256u : 512u)));
+    const uint32_t tmem_cols =
+        acc_cols <= 16 ? 32u : (acc_cols <= 32 ? 64u : (acc_cols <= 64 ? 128u : (acc_cols <= 128 ? 256u : 512u)));
     if (cw == 0) tmem_alloc(s_tmem, tmem_cols);
     tc_fence_before();
     asm volatile("bar.sync 1, %0;" ::"n"(kMelWarps * 32) : "memory");
     tc_fence_after();
     const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(s_tmem);
     GroupMax gmax{p.stage == B200A_STAGE_FEAT ? p.group_max : nullptr, -1, -CUDART_INF_F};
-    // conversion items: (chunk, row) with the row fastest, 128 per round over the four warps
+    // conversion items: (chunk, row) with the row fastest (8 consecutive lanes = one 256-byte block)
     constexpr int kItems = (Tc::kChunks - 1) * kRows, kRounds = (kItems + 127) / 128;
     const int erow = 16 * cw + (lane & 15);  // epilogue: thread i < 16 owns tile row 16 cw + i == TMEM lane 32 cw + i
 
@@ -1226,58 +1241,64 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
     int it = 0;
     int64_t o_prev = -1, g_prev = -1;
     for (int64_t base = u0; base < p.total_units; base += stride, ++it) {
-      const int b = it & 1;
-      mbar_wait_relaxed(s_full + b, (it >> 1) & 1);
+      const int b = it % NB;
+      const uint32_t use = (uint32_t)(it / NB) & 1;  // parity of this use of buffer b
+      mbar_wait(s_full + b, use);
       int64_t o_cur = -1, g_cur = -1;
-      if (cw < kEpi) {
+      if (cw < kEpi && erow < kRows) {
         o_cur = s_slot[b * kRows + erow];
         g_cur = s_grp[b * kRows + erow];
       }
-      if (it > 0) mbar_wait_relaxed(s_mma, (it - 1) & 1);  // the previous tile's MMAs no longer read the planes
       {
-        const float* pw = s_pow + (size_t)b * kRows * kPitch;
+        unsigned char* buf = s_a + (size_t)b * Tc::kOperand;
 #pragma unroll 2
         for (int rd = 0; rd < kRounds; ++rd) {
           const int item = rd * 128 + cw * 32 + lane;
-          if (item < kItems) {
-            const int chunk = item / kRows, row = item % kRows;
-            const float4 v0 = *reinterpret_cast<const float4*>(pw + row * kPitch + 8 * chunk);
-            const float4 v1 = *reinterpret_cast<const float4*>(pw + row * kPitch + 8 * chunk + 4);
-            uint4 hi, lo;
-            split_bf16x2(v0.x, v0.y, hi.x, lo.x);
-            split_bf16x2(v0.z, v0.w, hi.y, lo.y);
-            split_bf16x2(v1.x, v1.y, hi.z, lo.z);
-            split_bf16x2(v1.z, v1.w, hi.w, lo.w);
-            unsigned char* dst = s_a + (size_t)item * 16;  // chunk * kRows * 16 + row * 16
-            *reinterpret_cast<uint4*>(dst) = hi;
-            *reinterpret_cast<uint4*>(dst + kPlane) = lo;
+          const bool live = item < kItems;
+          const int chunk = item / kRows, row = item % kRows;
+          unsigned char* blk = buf + chunk * kStride + (row >> 3) * 256;
+          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+          if (live) {
+            v0 = *reinterpret_cast<const float4*>(blk + (row & 7) * 32);
+            v1 = *reinterpret_cast<const float4*>(blk + (row & 7) * 32 + 16);
+          }
+          uint4 hi, lo;
+          split_bf16x2(v0.x, v0.y, hi.x, lo.x);
+          split_bf16x2(v0.z, v0.w, hi.y, lo.y);
+          split_bf16x2(v1.x, v1.y, hi.z, lo.z);
+          split_bf16x2(v1.z, v1.w, hi.w, lo.w);
+          __syncwarp();  // the 8 rows of a block are 8 lanes of this warp: all reads before any write
+          if (live) {
+            *reinterpret_cast<uint4*>(blk + (row & 7) * 16) = hi;
+            *reinterpret_cast<uint4*>(blk + 128 + (row & 7) * 16) = lo;
           }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my plane writes -> async proxy
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(s_empty + b);
-        mbar_arrive(s_ready);
-      }
+      if (lane == 0) mbar_arrive(s_ready + b);
       if (cw == kMelWarps - 1) {
-        // ---- issue: D[t & 1][:, 2 n0 : 2 n0 + 2 N] += P_hi [F_hi | F_lo] + P_lo [F_hi | F_lo] per k-step ----
-        mbar_wait(s_ready, it & 1);
-        if (it >= 2) mbar_wait(s_tfree + b, ((it >> 1) & 1) ^ 1);  // tile it - 2 has been read out of this accumulator
+        // ---- issue: D[it & 1][:, 2 n0 : 2 n0 + 2 N] += P_hi [F_hi | F_lo] + P_lo [F_hi | F_lo] per k-step ----
+        mbar_wait(s_ready + b, use);
+        if (it >= 2) mbar_wait(s_tfree + (it & 1), ((it >> 1) & 1) ^ 1);  // tile it - 2 has left this accumulator
         tc_fence_after();
-        const uint32_t acc = tmem_d + (uint32_t)b * acc_cols;
+        const uint32_t acc = tmem_d + (uint32_t)(it & 1) * acc_cols;
+        const uint64_t a_off = (uint64_t)((uint32_t)b * (Tc::kOperand >> 4));
 #pragma unroll 3
         for (int s = 0; s < n_steps; ++s) {
           const TcIssue e = s_issue[s];
           if (elect_one()) {
-            umma_bf16(acc + e.col, e.a_hi, e.b, e.idesc, s > 0 ? 1u : 0u);  // step 0 spans every column: it clears D
-            umma_bf16(acc + e.col, e.a_lo, e.b, e.idesc, 1u);
+            umma_bf16(acc + e.col, e.a_hi + a_off, e.b, e.idesc, s > 0 ? 1u : 0u);  // step 0 spans every column
+            umma_bf16(acc + e.col, e.a_lo + a_off, e.b, e.idesc, 1u);
           }
         }
-        if (elect_one()) umma_commit(s_mma);
+        if (elect_one()) umma_commit(s_mma + b);
         __syncwarp();
       }
       if (cw < kEpi && it > 0) {  // the previous tile's accumulator, while the tensor core works on this one
+        // NB == 1: tile it could only be published (`full`, waited above) after the MMAs of tile it - 1 completed,
+        // and a second look at that barrier could race with the completion of tile it
+        if (NB > 1) mbar_wait(s_mma + (it - 1) % NB, (uint32_t)((it - 1) / NB) & 1);
         tc_fence_after();
         epilogue(it - 1, o_prev, g_prev);
       }
@@ -1285,7 +1306,7 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
       g_prev = g_cur;
     }
     if (cw < kEpi && it > 0) {
-      mbar_wait(s_mma, (it - 1) & 1);
+      mbar_wait(s_mma + (it - 1) % NB, (uint32_t)((it - 1) / NB) & 1);
       tc_fence_after();
       epilogue(it - 1, o_prev, g_prev);
     }
@@ -1362,12 +1383,14 @@ __global__ void prepare_tc_kernel(const float* __restrict__ fb, int n_bins, int 
 // The mel / MFCC-feature kernel: tcgen05 contraction when the prepared plan says the banded filterbank fits
 // shared memory (every real mel / linear filterbank does), mma.sync contraction otherwise.
 template <int POWER_MODE, int G, int HG>
-__global__ void __launch_bounds__((kWarps + kMelWarps) * 32, 1) stft_pow2_mel_kernel(const Pow2Params p) {
+__global__ void __launch_bounds__(TcGeo<G>::kThreads, 1) stft_pow2_mel_kernel(const Pow2Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // 512 threads start with 128 registers each: 8 x 32 x 192 + 4 x 32 x 96 + 4 x 32 x 24 <= 65536
+  constexpr int kMmaFftRegs = TcGeo<G>::kThreads == 512 ? 192 : kFftRegs;
   if (p.tc != nullptr && p.tc->ok)
     mel_body_tc<POWER_MODE, G, HG>(p, smem_raw);
   else
-    mel_body_mma<POWER_MODE, G, HG>(p, smem_raw);
+    mel_body_mma<POWER_MODE, G, HG, kMmaFftRegs>(p, smem_raw);
 }
 
 // ---- table preparation ------------------------------------------------------------------------
@@ -1506,12 +1529,10 @@ static int launch_power(const Pow2Params& p, cudaStream_t stream) {
   using Ge = Geo<G>;
   // the transform is latency bound: as many warps as shared memory (tile + staging buffer each) and the
   // register file (168 registers at 12 warps, no spills) allow
-  constexpr int NW = G == 8 ? 10 : 12;
-  const size_t smem = sizeof(float2) * (32 * 32 + NW * Ge::kTileF2) + sizeof(float) * NW * Ge::kStageFloats +
-                      sizeof(uint64_t) * NW;
-  static_assert(sizeof(float2) * (32 * 32 + NW * Ge::kTileF2) + sizeof(float) * NW * Ge::kStageFloats + 8 * NW <= 227 * 1024,
-                "power kernel shared memory");
-  auto kern = stft_pow2_power_kernel<POWER_MODE, G, HG, NW>;
+  constexpr int NW = 16;
+  constexpr bool kShare = true;  // the staged input lives in the warp's transpose tile
+  const size_t smem = sizeof(float2) * (32 * 32 + NW * Ge::kTileF2) + sizeof(uint64_t) * NW;
+  auto kern = stft_pow2_power_kernel<POWER_MODE, G, HG, NW, kShare>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return B200A_ECUDA;
   const int64_t grid = persistent_grid(p, NW);
@@ -1530,12 +1551,13 @@ static int launch_mel(const Pow2Params& p, cudaStream_t stream) {
                       sizeof(float4) * 32 * kFragSmemSteps;
   if (smem > 227 * 1024) return B200A_EUNSUPPORTED;
   static_assert(TcGeo<G>::kFixed + TcGeo<G>::kBBudget <= 227 * 1024 && TcGeo<G>::kBBudget >= 24 * 1024, "tcgen05 layout");
+  constexpr int kThreads = TcGeo<G>::kThreads;
   auto kern = stft_pow2_mel_kernel<POWER_MODE, G, HG>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return B200A_ECUDA;
-  const int64_t grid = persistent_grid(p);
+  const int64_t grid = persistent_grid(p, p.tc != nullptr ? TcGeo<G>::NW : kWarps);
   if (grid < 0) return B200A_ECUDA;
-  kern<<<(unsigned)grid, (kWarps + kMelWarps) * 32, p.tc != nullptr ? (size_t)227 * 1024 : smem, stream>>>(p);
+  kern<<<(unsigned)grid, kThreads, p.tc != nullptr ? (size_t)227 * 1024 : smem, stream>>>(p);
   return launch_status();
 }
 
