@@ -210,7 +210,7 @@ struct Pow2Params {
   const struct TcPlan* tc;     // tcgen05 contraction plan (nullptr: not available for this size)
   const unsigned char* tc_b;   // its banded bf16 B blocks
   int hop, pad, center, pad_mode, n_mels;
-  int stage, log_mels, bulk_ok;
+  int stage, log_mels, bulk_ok, stage_ok;
   float power, db_mult, db_amin, db_offset;
 };
 
@@ -333,9 +333,29 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
 
   float2 a[32];
   float2* grp_tile = tile + gi * Ge::kRegion;
+  bool from_stage = staged;
   if (staged) {
     mbar_wait(bar, parity);
     parity ^= 1;
+  } else if (!interior && p.stage_ok) {
+    // edge unit (padding / reflection / ragged end): the lanes gather the unit's whole span into the (idle)
+    // staging buffer with 4-byte asynchronous copies -- every sample once, all copies in flight together --
+    // and the unit then takes the same register-load path as a bulk-staged one
+    const int span = Ge::kNfft + (Ge::kFrames - 1) * p.hop;
+#pragma unroll 2
+    for (int n = lane; n < span; n += 32) {
+      int64_t src = s0 + n;
+      if (src < 0 || src >= p.length) src = source_index(t0 * p.hop + n, p.length, p.pad, half, p.pad_mode);
+      if (src >= 0)
+        cp_async4(stage + n, x + src);
+      else
+        stage[n] = 0.f;
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    from_stage = true;
+  }
+  if (from_stage) {
     if constexpr (HG >= 0) {  // G == 32: frame b is frame a shifted by HG lane-rows
       constexpr int kV = 32 + (HG >= 0 ? HG : 0);
       float v[kV];
@@ -364,7 +384,7 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
       a[brev5(j)] = make_float2(va * wreg[j], vb * wreg[j]);
     });
   } else {
-    // edge unit (padding / reflection / ragged end): gather through the group's tile region with a
+    // edge unit whose span does not fit the staging buffer: gather through the group's tile region with a
     // rolled loop so the index arithmetic is not replicated 64 times in the instruction stream
 #pragma unroll 1
     for (int j = 0; j < 32; ++j) {
@@ -1645,6 +1665,7 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
   p.bulk_ok = d->hop % 4 == 0 && (half + d->pad) % 4 == 0 && row_stride % 4 == 0 &&
               (reinterpret_cast<uintptr_t>(wave) & 15) == 0 &&
               d->n_fft + (frames_per_unit - 1) * (int64_t)d->hop <= stage_floats;
+  p.stage_ok = d->n_fft + (frames_per_unit - 1) * (int64_t)d->hop <= stage_floats;  // edge units gather into it
   const bool mel = stage >= B200A_STAGE_MEL;
   if (eo) {
     p.bulk_ok = d->hop % 4 == 0 && (half + d->pad) % 4 == 0 && row_stride % 4 == 0 &&
