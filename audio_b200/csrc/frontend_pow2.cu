@@ -342,11 +342,25 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
     // staging buffer with 4-byte asynchronous copies -- every sample once, all copies in flight together --
     // and the unit then takes the same register-load path as a bulk-staged one
     const int span = Ge::kNfft + (Ge::kFrames - 1) * p.hop;
-#pragma unroll 2
+    // 32-bit index arithmetic (the launch guarantees length + 2 pad + n_fft < 2^31): j indexes the constant
+    // pre-padded signal of `ext` samples, exactly as source_index() does in 64 bits
+    const int len = (int)p.length, ext = len + 2 * p.pad, j0 = (int)(t0 * p.hop) - half, mode = p.pad_mode;
+#pragma unroll 4
     for (int n = lane; n < span; n += 32) {
-      int64_t src = s0 + n;
-      if (src < 0 || src >= p.length) src = source_index(t0 * p.hop + n, p.length, p.pad, half, p.pad_mode);
-      if (src >= 0)
+      int j = j0 + n;
+      if ((unsigned)j >= (unsigned)ext) {
+        if (mode == B200A_PAD_REFLECT)
+          j = j < 0 ? -j : 2 * (ext - 1) - j;
+        else if (mode == B200A_PAD_REPLICATE)
+          j = j < 0 ? 0 : ext - 1;
+        else if (mode == B200A_PAD_CIRCULAR) {
+          j %= ext;
+          if (j < 0) j += ext;
+        } else
+          j = -1;
+      }
+      const int src = j - p.pad;
+      if (j >= 0 && (unsigned)src < (unsigned)len)
         cp_async4(stage + n, x + src);
       else
         stage[n] = 0.f;
@@ -1232,10 +1246,15 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
           v[q + 8] = w[q] + w[q + 8];
         }
         if (p.stage == B200A_STAGE_FEAT) {
+          // one thread owns a whole row here, so the logarithms are the epilogue's critical path: MUFU.LG2
+          // (2^-22 absolute on the log2, i.e. < 1e-5 dB) instead of the ~30-instruction log10f
           float mx = -CUDART_INF_F;
+          const float scale = p.log_mels ? 0.69314718055994531f : p.db_mult * 0.30102999566398120f;
+          const float offs = p.log_mels ? 0.f : p.db_offset;
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            v[q] = p.log_mels ? logf(v[q] + 1e-6f) : p.db_mult * log10f(fmaxf(v[q], p.db_amin)) - p.db_offset;
+            const float arg = p.log_mels ? v[q] + 1e-6f : fmaxf(v[q], p.db_amin);
+            v[q] = fmaf(scale, __log2f(arg), -offs);
             if (f0 + q < p.n_mels) mx = fmaxf(mx, v[q]);
           }
           gmax.add(g, mx, row_ok);
@@ -1665,7 +1684,8 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
   p.bulk_ok = d->hop % 4 == 0 && (half + d->pad) % 4 == 0 && row_stride % 4 == 0 &&
               (reinterpret_cast<uintptr_t>(wave) & 15) == 0 &&
               d->n_fft + (frames_per_unit - 1) * (int64_t)d->hop <= stage_floats;
-  p.stage_ok = d->n_fft + (frames_per_unit - 1) * (int64_t)d->hop <= stage_floats;  // edge units gather into it
+  p.stage_ok = d->n_fft + (frames_per_unit - 1) * (int64_t)d->hop <= stage_floats &&  // edge units gather into it
+               length + 2 * (int64_t)d->pad + d->n_fft < (int64_t)1 << 31;           // with 32-bit indices
   const bool mel = stage >= B200A_STAGE_MEL;
   if (eo) {
     p.bulk_ok = d->hop % 4 == 0 && (half + d->pad) % 4 == 0 && row_stride % 4 == 0 &&
