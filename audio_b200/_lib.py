@@ -45,6 +45,25 @@ class FrontendDesc(ctypes.Structure):
         return tuple(getattr(self, f) for f, _ in self._fields_)
 
 
+class KaldiDesc(ctypes.Structure):
+    """Mirror of ``b200a_kaldi_desc``."""
+
+    _fields_ = [
+        ("window_size", c_int32),
+        ("window_shift", c_int32),
+        ("padded_size", c_int32),
+        ("snip_edges", c_int32),
+        ("remove_dc_offset", c_int32),
+        ("preemphasis", c_float),
+        ("energy_mode", c_int32),
+        ("energy_floor", c_float),
+        ("energy_col", c_int32),
+        ("out_width", c_int32),
+        ("out_col0", c_int32),
+        ("use_log", c_int32),
+    ]
+
+
 _SIGNATURES = {
     "b200a_version": (ctypes.c_int, []),
     "b200a_strerror": (c_char_p, [ctypes.c_int]),
@@ -74,6 +93,12 @@ _SIGNATURES = {
         ctypes.c_int,
         [c_void_p, c_int64, c_int64, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p],
     ),
+    "b200a_kaldi_num_frames": (c_int64, [c_int64, c_int32, c_int32, c_int32]),
+    "b200a_kaldi_run": (
+        ctypes.c_int,
+        [POINTER(KaldiDesc), POINTER(FrontendDesc), c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p],
+    ),
+    "b200a_subtract_column_mean": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "b200a_fill_f32": (ctypes.c_int, [c_void_p, c_int64, c_float, c_void_p]),
     "b200a_ratio_f32": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "b200a_resample_workspace_bytes": (c_size_t, [c_int32, c_int32]),

@@ -7,7 +7,8 @@ namespace b200a {
 int validate_desc(const b200a_frontend_desc* d);
 int frontend_prepare_impl(const b200a_frontend_desc*, const float*, const float*, const float*, void*, size_t, cudaStream_t);
 int frontend_run_generic(const b200a_frontend_desc*, const void*, int, const float*, int64_t, int64_t, int64_t, int64_t,
-                         float*, float*, int64_t, cudaStream_t);
+                         float*, float*, int64_t, cudaStream_t, const b200a_kaldi_desc* = nullptr);
+int subtract_column_mean_impl(float*, int64_t, int64_t, int64_t, cudaStream_t);
 int frontend_run_pow2(const b200a_frontend_desc*, const void*, int, const float*, int64_t, int64_t, int64_t, int64_t,
                       float*, float*, int64_t, cudaStream_t);  // returns B200A_EUNSUPPORTED when not applicable
 size_t pow2_workspace_extra(const b200a_frontend_desc*);
@@ -147,6 +148,49 @@ int b200a_amplitude_to_db(const float* x, int64_t groups, int64_t group_elems, f
   if (x == nullptr || out == nullptr || groups < 0 || group_elems < 0) return B200A_EINVAL;
   return amplitude_to_db_impl(x, groups, group_elems, multiplier, amin, offset, top_db, scratch, out,
                               static_cast<cudaStream_t>(stream));
+}
+
+int64_t b200a_kaldi_num_frames(int64_t length, int32_t window_size, int32_t window_shift, int32_t snip_edges) {
+  if (length < 0 || window_size < 1 || window_shift < 1) return -1;
+  if (snip_edges) return length < window_size ? 0 : 1 + (length - window_size) / window_shift;
+  return (length + window_shift / 2) / window_shift;
+}
+
+int b200a_kaldi_run(const b200a_kaldi_desc* kaldi, const b200a_frontend_desc* desc, const void* workspace,
+                    int32_t stage, const float* wave, int64_t rows, int64_t length, int64_t row_stride,
+                    float* out, b200a_stream stream) {
+  if (kaldi == nullptr) return B200A_EINVAL;
+  int rc = validate_desc(desc);
+  if (rc != B200A_OK) return rc;
+  if (kaldi->window_size < 2 || kaldi->window_shift < 1 || kaldi->padded_size < kaldi->window_size ||
+      kaldi->padded_size % 2 != 0)
+    return B200A_EINVAL;
+  if (desc->n_fft != kaldi->padded_size || desc->win_length != kaldi->padded_size || desc->hop != kaldi->window_shift ||
+      desc->center != 0 || desc->pad != 0 || !desc->onesided)
+    return B200A_EINVAL;
+  if (stage != B200A_STAGE_POWER && stage != B200A_STAGE_MEL) return B200A_EINVAL;
+  if (stage == B200A_STAGE_MEL && desc->n_mels <= 0) return B200A_EINVAL;
+  if (!(desc->power > 0.f) || !(kaldi->preemphasis >= 0.f && kaldi->preemphasis <= 1.f)) return B200A_EINVAL;
+  if (kaldi->energy_mode < 0 || kaldi->energy_mode > 2 || kaldi->energy_floor < 0.f) return B200A_EINVAL;
+  const int values = stage == B200A_STAGE_MEL ? desc->n_mels : desc->n_fft / 2 + 1;
+  if (kaldi->out_col0 < 0 || kaldi->out_col0 + values > kaldi->out_width ||
+      kaldi->energy_col >= kaldi->out_width)
+    return B200A_EINVAL;
+  if (rows == 0) return B200A_OK;
+  if (workspace == nullptr || wave == nullptr || out == nullptr) return B200A_EINVAL;
+  if (rows < 0 || length < 0 || row_stride < length) return B200A_EINVAL;
+  if (length < kaldi->window_size) return B200A_ESHORT;  // kaldi.py:142-144
+  const int64_t frames = b200a_kaldi_num_frames(length, kaldi->window_size, kaldi->window_shift, kaldi->snip_edges);
+  if (frames < 1) return B200A_ESHORT;
+  return frontend_run_generic(desc, workspace, stage, wave, rows, length, row_stride, frames, out, nullptr, 1,
+                              static_cast<cudaStream_t>(stream), kaldi);
+}
+
+int b200a_subtract_column_mean(float* x, int64_t rows, int64_t frames, int64_t width, b200a_stream stream) {
+  if (rows < 0 || frames < 0 || width < 0) return B200A_EINVAL;
+  if (rows == 0 || frames == 0 || width == 0) return B200A_OK;
+  if (x == nullptr) return B200A_EINVAL;
+  return subtract_column_mean_impl(x, rows, frames, width, static_cast<cudaStream_t>(stream));
 }
 
 int b200a_ratio_f32(const float* pairs, int64_t n, float* out, b200a_stream stream) {

@@ -105,7 +105,29 @@ struct GenericParams {
   int stage;  // b200a_stage
   int log_mels;
   float power, db_mult, db_amin, db_offset;
+  // output row geometry (Kaldi features put the frame energy next to the spectral values)
+  int out_width, out_col0;
+  // Kaldi framing and per-frame conditioning (compliance/kaldi.py:44-83, :153-226); kaldi == 0: torch.stft framing
+  int kaldi, k_win, k_snip, k_dc, k_energy_mode, k_energy_col, k_log;
+  float k_preemph, k_energy_floor;
 };
+
+constexpr float kKaldiEps = 1.1920928955078125e-07f;  // numeric_limits<float>::epsilon(), kaldi.py:21-22
+
+// Sample n of Kaldi frame t (kaldi.py:_get_strided).  snip_edges: frames lie inside the signal.  Otherwise the
+// signal is extended by its mirror image on both sides (x[-1-j] = x[j], x[L+j] = x[L-1-j]) and frame t starts
+// at t*shift - (win/2 - shift/2).
+__device__ __forceinline__ float kaldi_sample(const float* __restrict__ x, int64_t length, int64_t t, int n, int win,
+                                              int shift, int snip) {
+  int64_t j = t * shift + n;
+  if (!snip) {
+    j -= win / 2 - shift / 2;
+    if (j < 0) j = -1 - j;
+    if (j >= length) j = 2 * length - 1 - j;
+    if (j < 0 || j >= length) return 0.f;  // only for signals shorter than half a frame
+  }
+  return x[j];
+}
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -136,6 +158,58 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const GenericParams p
 
   for (int i = tid; i < N; i += nthr) tw[i] = p.twiddle[i];
 
+  if (p.kaldi) {
+    // ---- Kaldi conditioning: raw frames -> (DC removal) -> [raw energy] -> pre-emphasis -> window -> [energy] ----
+    float* raw = reinterpret_cast<float*>(buf1);   // [pair][n][2]
+    float* cond = reinterpret_cast<float*>(buf0);  // same layout: z[n] = frame_a[n] + i frame_b[n]
+    const int win = p.k_win;
+    for (int o = tid; o < pairs * N; o += nthr) {
+      const int pr = o / N, n = o - pr * N;
+      const int64_t ta = t0 + 2 * pr, tb = ta + 1;
+      float a = 0.f, b = 0.f;
+      if (n < win) {
+        if (ta < p.frames) a = kaldi_sample(x, p.length, ta, n, win, p.hop, p.k_snip);
+        if (tb < p.frames) b = kaldi_sample(x, p.length, tb, n, win, p.hop, p.k_snip);
+      }
+      buf1[o] = make_float2(a, b);
+    }
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    for (int f = warp; f < 2 * pairs; f += nwarps) {  // one warp per frame
+      const float* fr = raw + (size_t)(f >> 1) * N * 2 + (f & 1);
+      float* dstf = cond + (size_t)(f >> 1) * N * 2 + (f & 1);
+      float mean = 0.f;
+      if (p.k_dc) {
+        float sum = 0.f;
+        for (int n = lane; n < win; n += 32) sum += fr[2 * n];
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mean = sum / (float)win;
+      }
+      float energy = 0.f;
+      if (p.k_energy_mode == 1)
+        for (int n = lane; n < win; n += 32) {
+          const float v = fr[2 * n] - mean;
+          energy = fmaf(v, v, energy);
+        }
+      for (int n = lane; n < N; n += 32) {
+        float v = 0.f;
+        if (n < win) {
+          const float cur = fr[2 * n] - mean, prev = fr[2 * (n > 0 ? n - 1 : 0)] - mean;
+          v = (cur - p.k_preemph * prev) * p.window[n];
+        }
+        dstf[2 * n] = v;
+        if (p.k_energy_mode == 2) energy = fmaf(v, v, energy);
+      }
+      const int64_t t = t0 + f;
+      if (p.k_energy_mode != 0 && p.k_energy_col >= 0 && t < p.frames) {
+        for (int o = 16; o > 0; o >>= 1) energy += __shfl_xor_sync(0xffffffffu, energy, o);
+        float le = logf(fmaxf(energy, kKaldiEps));
+        if (p.k_energy_floor > 0.f) le = fmaxf(le, logf(p.k_energy_floor));
+        if (lane == 0) p.out[(row * p.frames + t) * p.out_width + p.k_energy_col] = le;
+      }
+    }
+    __syncthreads();
+  } else
   // ---- gather + window: z[n] = w[n] * (frame_a[n] + i frame_b[n]) --------------------------
   for (int o = tid; o < pairs * N; o += nthr) {
     const int pr = o / N, n = o - pr * N;
@@ -207,11 +281,17 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const GenericParams p
       if (ta < p.frames) o2[(row * p.frames + ta) * n_bins + k] = make_float2(are, aim);
       if (tb < p.frames) o2[(row * p.frames + tb) * n_bins + k] = make_float2(bre, bim);
     } else {
-      const float pa = spectral_power(are, aim, p.power);
-      const float pb = spectral_power(bre, bim, p.power);
+      float pa = spectral_power(are, aim, p.power);
+      float pb = spectral_power(bre, bim, p.power);
       if (p.stage == B200A_STAGE_POWER) {
-        if (ta < p.frames) p.out[(row * p.frames + ta) * n_bins + k] = pa;
-        if (tb < p.frames) p.out[(row * p.frames + tb) * n_bins + k] = pb;
+        if (p.k_log) {  // Kaldi spectrogram: log(max(|X|^2, eps)), kaldi.py:310
+          pa = logf(fmaxf(pa, kKaldiEps));
+          pb = logf(fmaxf(pb, kKaldiEps));
+        }
+        if (p.out_col0 + k != p.k_energy_col) {
+          if (ta < p.frames) p.out[(row * p.frames + ta) * p.out_width + p.out_col0 + k] = pa;
+          if (tb < p.frames) p.out[(row * p.frames + tb) * p.out_width + p.out_col0 + k] = pb;
+        }
       } else {
         tile_pow[(size_t)(2 * pr) * n_bins + k] = pa;
         tile_pow[(size_t)(2 * pr + 1) * n_bins + k] = pb;
@@ -228,7 +308,7 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const GenericParams p
     const int64_t t = t0 + f;
     if (t >= p.frames) break;
     const float* pw = tile_pow + (size_t)f * n_bins;
-    float* orow = p.out + (row * p.frames + t) * p.n_mels;
+    float* orow = p.out + (row * p.frames + t) * p.out_width + p.out_col0;
     for (int m = lane; m < p.n_mels; m += 32) {
       const int2 band = p.bands[m];
       float acc = 0.f;
@@ -237,6 +317,7 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const GenericParams p
         acc = p.log_mels ? logf(acc + 1e-6f) : p.db_mult * log10f(fmaxf(acc, p.db_amin)) - p.db_offset;
         local_max = fmaxf(local_max, acc);
       }
+      if (p.k_log) acc = logf(fmaxf(acc, kKaldiEps));  // Kaldi fbank, kaldi.py:629-631
       orow[m] = acc;
     }
   }
@@ -416,7 +497,8 @@ int frontend_prepare_impl(const b200a_frontend_desc* d, const float* window, con
 
 int frontend_run_generic(const b200a_frontend_desc* d, const void* ws, int stage, const float* wave,
                          int64_t rows, int64_t length, int64_t row_stride, int64_t frames, float* out,
-                         float* group_max, int64_t rows_per_group, cudaStream_t stream) {
+                         float* group_max, int64_t rows_per_group, cudaStream_t stream,
+                         const b200a_kaldi_desc* kd) {
   const WsLayout l = ws_layout(*d);
   const unsigned char* base = static_cast<const unsigned char*>(ws);
   GenericParams p{};
@@ -447,6 +529,22 @@ int frontend_run_generic(const b200a_frontend_desc* d, const void* ws, int stage
   p.db_mult = d->db_multiplier;
   p.db_amin = d->db_amin;
   p.db_offset = d->db_offset;
+  p.out_width = stage >= B200A_STAGE_MEL ? p.n_mels : p.n_bins;
+  p.out_col0 = 0;
+  p.k_energy_col = -1;
+  if (kd != nullptr) {
+    p.kaldi = 1;
+    p.k_win = kd->window_size;
+    p.k_snip = kd->snip_edges;
+    p.k_dc = kd->remove_dc_offset;
+    p.k_preemph = kd->preemphasis;
+    p.k_energy_mode = kd->energy_col >= 0 ? kd->energy_mode : 0;
+    p.k_energy_floor = kd->energy_floor;
+    p.k_energy_col = kd->energy_col;
+    p.k_log = kd->use_log;
+    p.out_width = kd->out_width;
+    p.out_col0 = kd->out_col0;
+  }
   // frames per CTA: enough work for 256 threads, at most ~48 KB of ping-pong buffers
   int pairs = (int)(49152 / (16 * (size_t)d->n_fft));
   if (pairs < 1) pairs = 1;

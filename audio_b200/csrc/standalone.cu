@@ -105,4 +105,33 @@ int amplitude_to_db_impl(const float* x, int64_t groups, int64_t group_elems, fl
   return launch_status();
 }
 
+// x[r][t][c] -= mean over t.  One CTA per (matrix, group of 32 columns): warp w sums frames w, w+8, ... of its
+// 32 columns (coalesced rows), the partial sums meet in shared memory, then the same sweep subtracts.
+__global__ void __launch_bounds__(256) subtract_column_mean_kernel(float* __restrict__ x, int64_t frames, int64_t width,
+                                                                   int64_t col_groups) {
+  __shared__ float s_part[8][32];
+  const int64_t r = blockIdx.x / col_groups, cg = blockIdx.x - r * col_groups;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c = cg * 32 + lane;
+  float* base = x + r * frames * width;
+  float sum = 0.f;
+  if (c < width)
+    for (int64_t t = warp; t < frames; t += 8) sum += base[t * width + c];
+  s_part[warp][lane] = sum;
+  __syncthreads();
+  float mean = 0.f;
+  for (int w = 0; w < 8; ++w) mean += s_part[w][lane];
+  mean /= (float)frames;
+  if (c < width)
+    for (int64_t t = warp; t < frames; t += 8) base[t * width + c] -= mean;
+}
+
+int subtract_column_mean_impl(float* x, int64_t rows, int64_t frames, int64_t width, cudaStream_t stream) {
+  const int64_t col_groups = (width + 31) / 32;
+  const int64_t grid = rows * col_groups;
+  if (grid > 0x7fffffffLL) return B200A_EUNSUPPORTED;
+  subtract_column_mean_kernel<<<(unsigned)grid, 256, 0, stream>>>(x, frames, width, col_groups);
+  return launch_status();
+}
+
 }  // namespace b200a

@@ -168,6 +168,46 @@ int b200a_fill_f32(float* dst, int64_t n, float value, b200a_stream stream);
  */
 int b200a_ratio_f32(const float* pairs, int64_t n, float* out, b200a_stream stream);
 
+/* ---- Kaldi-compatible features (compliance/kaldi.py: spectrogram :229-316, fbank :514-645, mfcc :669-813) -------- */
+/*
+ * Per-frame conditioning and output placement of the Kaldi front end; the transform itself (window, FFT size,
+ * |X| or |X|^2, mel matrix) is described by a b200a_frontend_desc with center = 0, n_fft = win_length = padded_size,
+ * hop = window_shift, and a workspace prepared by b200a_frontend_prepare from
+ *   window : [padded_size]  the Kaldi window (_feature_window_function, :86-113) followed by zeros (:206-211)
+ *   fb     : [padded_size/2+1][n_mels]  get_mel_banks(...) transposed, last row zero (:436-511, :623-624), or NULL.
+ */
+typedef struct b200a_kaldi_desc {
+  int32_t window_size;      /* samples per frame, int(sample_frequency * frame_length * 0.001)          (:139) */
+  int32_t window_shift;     /* int(sample_frequency * frame_shift * 0.001)                             (:138) */
+  int32_t padded_size;      /* FFT size: next power of two of window_size, or window_size; even        (:140) */
+  int32_t snip_edges;       /* 1: only frames inside the signal; 0: mirror-extended signal             (:44-83) */
+  int32_t remove_dc_offset; /* subtract each frame's mean                                              (:181-184) */
+  float preemphasis;        /* s[j] -= c * s[max(0, j-1)]; 0 disables                                  (:191-197) */
+  int32_t energy_mode;      /* 0 none, 1 raw (after DC removal, before pre-emphasis), 2 after the window (:186-189,:213-215) */
+  float energy_floor;       /* log energy >= log(energy_floor); 0: no floor                            (:116-123) */
+  int32_t energy_col;       /* output column that receives the log energy, -1: none                   */
+  int32_t out_width;        /* floats per output frame                                                 */
+  int32_t out_col0;         /* output column of the first spectral / mel value                         */
+  int32_t use_log;          /* log(max(v, FLT_EPSILON)) on the spectral / mel values                   (:310, :629-631) */
+} b200a_kaldi_desc;
+
+/* m of _get_strided (:62-68): 1 + (L - win)/shift (0 if L < win) when snip_edges, else (L + shift/2)/shift. */
+int64_t b200a_kaldi_num_frames(int64_t length, int32_t window_size, int32_t window_shift, int32_t snip_edges);
+
+/*
+ * Fused Kaldi front end: frames -> DC removal -> [raw log energy] -> pre-emphasis -> window -> zero pad -> rFFT ->
+ * |X|^power -> [mel] -> [log] for `rows` signals.  stage = B200A_STAGE_POWER (spectrogram) or B200A_STAGE_MEL (fbank).
+ *   out : [rows][m][out_width]; spectral value k goes to column out_col0 + k unless that is energy_col.
+ * Dither is not offered: the reference draws it with torch.randn per frame element (:176-178), which no
+ * other generator reproduces; callers pass dither = 0.
+ */
+int b200a_kaldi_run(const b200a_kaldi_desc* kaldi, const b200a_frontend_desc* desc, const void* workspace,
+                    int32_t stage, const float* wave, int64_t rows, int64_t length, int64_t row_stride,
+                    float* out, b200a_stream stream);
+
+/* x[r][t][c] -= mean_t x[r][t][c], in place, for each of `rows` feature matrices (_subtract_column_mean, :219-226). */
+int b200a_subtract_column_mean(float* x, int64_t rows, int64_t frames, int64_t width, b200a_stream stream);
+
 /* ---- polyphase sinc resampler ------------------------------------------------------------- */
 /* Workspace bytes for b200a_resample_prepare (per-phase tap supports + compacted taps). */
 size_t b200a_resample_workspace_bytes(int32_t new_r, int32_t taps);
