@@ -10,7 +10,8 @@ int frontend_run_generic(const b200a_frontend_desc*, const void*, int, const flo
                          float*, float*, int64_t, cudaStream_t, const b200a_kaldi_desc* = nullptr);
 int subtract_column_mean_impl(float*, int64_t, int64_t, int64_t, cudaStream_t);
 int frontend_run_pow2(const b200a_frontend_desc*, const void*, int, const float*, int64_t, int64_t, int64_t, int64_t,
-                      float*, float*, int64_t, cudaStream_t);  // returns B200A_EUNSUPPORTED when not applicable
+                      float*, float*, int64_t, cudaStream_t,
+                      const b200a_kaldi_desc* = nullptr);  // returns B200A_EUNSUPPORTED when not applicable
 size_t pow2_workspace_extra(const b200a_frontend_desc*);
 int pow2_prepare(const b200a_frontend_desc*, void*, size_t, cudaStream_t);
 int mfcc_finish_impl(const b200a_frontend_desc*, const void*, const float*, int64_t, int64_t, const float*, int64_t, float,
@@ -182,8 +183,10 @@ int b200a_kaldi_run(const b200a_kaldi_desc* kaldi, const b200a_frontend_desc* de
   if (length < kaldi->window_size) return B200A_ESHORT;  // kaldi.py:142-144
   const int64_t frames = b200a_kaldi_num_frames(length, kaldi->window_size, kaldi->window_shift, kaldi->snip_edges);
   if (frames < 1) return B200A_ESHORT;
-  return frontend_run_generic(desc, workspace, stage, wave, rows, length, row_stride, frames, out, nullptr, 1,
-                              static_cast<cudaStream_t>(stream), kaldi);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  rc = frontend_run_pow2(desc, workspace, stage, wave, rows, length, row_stride, frames, out, nullptr, 1, s, kaldi);
+  if (rc != B200A_EUNSUPPORTED) return rc;
+  return frontend_run_generic(desc, workspace, stage, wave, rows, length, row_stride, frames, out, nullptr, 1, s, kaldi);
 }
 
 int b200a_subtract_column_mean(float* x, int64_t rows, int64_t frames, int64_t width, b200a_stream stream) {

@@ -47,6 +47,8 @@ namespace b200a {
 
 namespace {
 
+constexpr float kKaldiEps = 1.1920928955078125e-07f;  // numeric_limits<float>::epsilon(), kaldi.py:21-22
+constexpr int kPadSymmetric = 4;  // internal pad mode: x[-1-j] = x[j], x[L+j] = x[L-1-j] (Kaldi snip_edges = false)
 constexpr int kWarps = 8;     // transform warps per CTA
 constexpr int kMelWarps = 4;  // contraction warps per CTA (mel kernel)
 constexpr int kMaxItems = 64;  // filter groups (of 8) per contraction
@@ -211,8 +213,18 @@ struct Pow2Params {
   const unsigned char* tc_b;   // its banded bf16 B blocks
   int hop, pad, center, pad_mode, n_mels;
   int stage, log_mels, bulk_ok, stage_ok;
+  // output row geometry: value m of frame t goes to out[(row * frames + t) * out_width + out_col0 + m]
+  int out_width, out_col0, out_vec;  // out_vec: floats every row start is aligned to (1, 2 or 4)
+  // Kaldi framing / per-frame conditioning (compliance/kaldi.py:44-83, :153-216); kaldi == 0: torch.stft framing
+  int kaldi, k_off, k_win, k_dc, k_energy_mode, k_energy_col, k_log;
+  float k_preemph, k_energy_floor;
   float power, db_mult, db_amin, db_offset;
 };
+
+// samples before t * hop where frame t starts: n_fft/2 (torch.stft center), 0, or Kaldi's win/2 - shift/2
+__device__ __forceinline__ int frame_lead(const Pow2Params& p, int n_fft) {
+  return p.kaldi ? p.k_off : (p.center ? n_fft / 2 : 0);
+}
 
 template <int POWER_MODE>  // 2: |.|^2, 0: general exponent (1 handled inside)
 __device__ __forceinline__ float pow_of(float re, float im, float power) {
@@ -337,7 +349,7 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
   if (staged) {
     mbar_wait(bar, parity);
     parity ^= 1;
-  } else if (!interior && p.stage_ok) {
+  } else if ((!interior || p.kaldi) && p.stage_ok) {
     // edge unit (padding / reflection / ragged end): the lanes gather the unit's whole span into the (idle)
     // staging buffer with 4-byte asynchronous copies -- every sample once, all copies in flight together --
     // and the unit then takes the same register-load path as a bulk-staged one
@@ -353,6 +365,8 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
           j = j < 0 ? -j : 2 * (ext - 1) - j;
         else if (mode == B200A_PAD_REPLICATE)
           j = j < 0 ? 0 : ext - 1;
+        else if (mode == kPadSymmetric)
+          j = j < 0 ? -1 - j : 2 * ext - 1 - j;
         else if (mode == B200A_PAD_CIRCULAR) {
           j %= ext;
           if (j < 0) j += ext;
@@ -369,7 +383,67 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
     __syncwarp();
     from_stage = true;
   }
-  if (from_stage) {
+  if (from_stage && p.kaldi) {
+    // Kaldi conditioning of the two staged frames (sample n = l + G j, n < win): DC removal, [raw log energy],
+    // pre-emphasis s[n] - c s[max(n - 1, 0)], window (zero beyond win), [log energy after the window]
+    const float* fa = stage + 2 * gi * p.hop;
+    const float* fb = fa + p.hop;
+    const int win = p.k_win;
+    float ma = 0.f, mb = 0.f;
+    if (p.k_dc) {
+#pragma unroll 4
+      for (int n = l; n < win; n += G) {
+        ma += fa[n];
+        mb += fb[n];
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) {
+        ma += __shfl_xor_sync(0xffffffffu, ma, o);
+        mb += __shfl_xor_sync(0xffffffffu, mb, o);
+      }
+      ma /= (float)win;
+      mb /= (float)win;
+    }
+    float ea = 0.f, eb = 0.f;
+    if (p.k_energy_mode == 1) {
+#pragma unroll 4
+      for (int n = l; n < win; n += G) {
+        const float da = fa[n] - ma, db = fb[n] - mb;
+        ea = fmaf(da, da, ea);
+        eb = fmaf(db, db, eb);
+      }
+    }
+    const float c = p.k_preemph;
+    static_for<32>([&](auto ji) {
+      constexpr int j = decltype(ji)::value;
+      const int n = l + G * j;
+      float va = 0.f, vb = 0.f;
+      if (n < win) {
+        const int np = n > 0 ? n - 1 : 0;
+        va = ((fa[n] - ma) - c * (fa[np] - ma)) * wreg[j];
+        vb = ((fb[n] - mb) - c * (fb[np] - mb)) * wreg[j];
+      }
+      a[brev5(j)] = make_float2(va, vb);
+      if (p.k_energy_mode == 2) {  // wreg carries the un-packing's 1/2
+        ea = fmaf(2.f * va, 2.f * va, ea);
+        eb = fmaf(2.f * vb, 2.f * vb, eb);
+      }
+    });
+    if (p.k_energy_mode != 0) {
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) {
+        ea += __shfl_xor_sync(0xffffffffu, ea, o);
+        eb += __shfl_xor_sync(0xffffffffu, eb, o);
+      }
+      if (l == 0) {
+        const float fl = p.k_energy_floor > 0.f ? logf(p.k_energy_floor) : -CUDART_INF_F;
+        float* e_out = p.out + (row * p.frames + ta) * p.out_width + p.k_energy_col;
+        if (has_a) e_out[0] = fmaxf(logf(fmaxf(ea, kKaldiEps)), fl);
+        if (has_b) e_out[p.out_width] = fmaxf(logf(fmaxf(eb, kKaldiEps)), fl);
+      }
+    }
+    __syncwarp();  // every lane has consumed the staging buffer
+  } else if (from_stage) {
     if constexpr (HG >= 0) {  // G == 32: frame b is frame a shifted by HG lane-rows
       constexpr int kV = 32 + (HG >= 0 ? HG : 0);
       float v[kV];
@@ -506,7 +580,7 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_pow2_power_kernel(const Pow2P
   uint64_t* bar = s_bar + warp;
   float wreg[32];
   load_window<G>(p, lane, wreg);
-  const int half = p.center ? Ge::kNfft / 2 : 0;
+  const int half = frame_lead(p, Ge::kNfft);
   const int gi = lane / G, l = lane % G;
   uint32_t parity = 0;
   bool staged = false;
@@ -544,7 +618,6 @@ __device__ __forceinline__ void contract_tile(const Pow2Params& p, const MelPlan
                                               const int64_t* slot, const int64_t* grp, GroupMax& gmax) {
   const int r = lane >> 2, c = lane & 3;
   const int cnt = s_plan->warp_cnt[mw];
-  const int width = p.n_mels;
   const int64_t o_lo = slot[r], o_hi = slot[r + 8];
   const int64_t g_lo = grp[r], g_hi = grp[r + 8];
   for (int ii = 0; ii < cnt; ++ii) {
@@ -576,6 +649,10 @@ __device__ __forceinline__ void contract_tile(const Pow2Params& p, const MelPlan
     for (int q = 0; q < 4; ++q) d[q] = d0[q] + (d1[q] + d2[q]);
     const int n0 = 8 * mi.tile + 2 * c;
     const bool n0_ok = n0 < p.n_mels, n1_ok = n0 + 1 < p.n_mels;
+    if (p.k_log) {  // Kaldi fbank: log(max(mel, FLT_EPSILON)), kaldi.py:629-631
+#pragma unroll
+      for (int q = 0; q < 4; ++q) d[q] = logf(fmaxf(d[q], kKaldiEps));
+    }
     if (p.stage == B200A_STAGE_FEAT) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
@@ -585,7 +662,7 @@ __device__ __forceinline__ void contract_tile(const Pow2Params& p, const MelPlan
       gmax.add(g_lo, m_lo, o_lo >= 0);
       gmax.add(g_hi, m_hi, o_hi >= 0);
     }
-    const bool vec = n1_ok && (width & 1) == 0;  // 8-byte aligned pair
+    const bool vec = n1_ok && p.out_vec >= 2;  // 8-byte aligned pair
     if (o_lo >= 0) {
       if (vec) *reinterpret_cast<float2*>(p.out + o_lo + n0) = make_float2(d[0], d[1]);
       else {
@@ -654,7 +731,7 @@ __device__ __forceinline__ void mel_body_mma(const Pow2Params& p, unsigned char*
 
   const int64_t stride = (int64_t)gridDim.x * kWarps;
   const int64_t u0 = (int64_t)blockIdx.x * kWarps;
-  const int width = p.n_mels;
+  const int width = p.out_width;
 
   if (warp < kWarps) {
     // =============================== transform warps ===========================================
@@ -664,7 +741,7 @@ __device__ __forceinline__ void mel_body_mma(const Pow2Params& p, unsigned char*
     uint64_t* bar = s_bar + warp;
     float wreg[32];
     load_window<G>(p, lane, wreg);
-    const int half = p.center ? Ge::kNfft / 2 : 0;
+    const int half = frame_lead(p, Ge::kNfft);
     const int gi = lane / G, l = lane % G;
     uint32_t parity = 0;
     bool staged = false;
@@ -699,7 +776,7 @@ __device__ __forceinline__ void mel_body_mma(const Pow2Params& p, unsigned char*
       }
       if (l == 0) {
         const int64_t ta = cur.ub * Ge::kFrames + 2 * gi;
-        const int64_t oa = (cur.row * p.frames + ta) * (int64_t)width;
+        const int64_t oa = (cur.row * p.frames + ta) * (int64_t)width + p.out_col0;
         s_slot[b * kSlots + slot_a] = (valid && ta < p.frames) ? oa : -1;
         s_slot[b * kSlots + slot_a + 1] = (valid && ta + 1 < p.frames) ? oa + width : -1;
         const int64_t g = cur.row / p.rows_per_group;
@@ -1153,7 +1230,7 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
 
   const int64_t stride = (int64_t)gridDim.x * NW;
   const int64_t u0 = (int64_t)blockIdx.x * NW;
-  const int width = p.n_mels;
+  const int width = p.out_width;
 
   if (warp < NW) {
     // =============================== transform warps ===========================================
@@ -1163,7 +1240,7 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
     uint64_t* bar = s_bar + warp;
     float wreg[32];
     load_window<G>(p, lane, wreg);
-    const int half = p.center ? Ge::kNfft / 2 : 0;
+    const int half = frame_lead(p, Ge::kNfft);
     const int gi = lane / G, l = lane % G;
     uint32_t parity = 0;
     bool staged = false;
@@ -1203,7 +1280,7 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
       }
       if (l == 0) {
         const int64_t ta = cur.ub * Ge::kFrames + 2 * gi;
-        const int64_t oa = (cur.row * p.frames + ta) * (int64_t)width;
+        const int64_t oa = (cur.row * p.frames + ta) * (int64_t)width + p.out_col0;
         s_slot[b * kRows + row_a] = (valid && ta < p.frames) ? oa : -1;
         s_slot[b * kRows + row_a + 1] = (valid && ta + 1 < p.frames) ? oa + width : -1;
         const int64_t g = cur.row / p.rows_per_group;
@@ -1245,6 +1322,10 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
           v[q] = u[q] + u[q + 8];
           v[q + 8] = w[q] + w[q + 8];
         }
+        if (p.k_log) {  // Kaldi fbank: log(max(mel, FLT_EPSILON)), kaldi.py:629-631
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0.69314718055994531f * __log2f(fmaxf(v[q], kKaldiEps));
+        }
         if (p.stage == B200A_STAGE_FEAT) {
           // one thread owns a whole row here, so the logarithms are the epilogue's critical path: MUFU.LG2
           // (2^-22 absolute on the log2, i.e. < 1e-5 dB) instead of the ~30-instruction log10f
@@ -1261,7 +1342,7 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
         }
         if (row_ok) {
           float* dst = p.out + o + f0;
-          if ((width & 3) == 0 && f0 + 16 <= p.n_mels) {
+          if (p.out_vec >= 4 && f0 + 16 <= p.n_mels) {
 #pragma unroll
             for (int q = 0; q < 16; q += 4)
               *reinterpret_cast<float4*>(dst + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
@@ -1603,7 +1684,7 @@ static int launch_mel(const Pow2Params& p, cudaStream_t stream) {
 template <int POWER_MODE, int G>
 static int launch_g(const Pow2Params& p, bool mel, cudaStream_t stream) {
   if constexpr (G == 32) {
-    if (p.bulk_ok && p.hop == 256)  // frame b = frame a shifted by 8 lane-rows: shared register loads
+    if (p.bulk_ok && p.hop == 256 && !p.kaldi)  // frame b = frame a shifted by 8 lane-rows: shared register loads
       return mel ? launch_mel<POWER_MODE, 32, 8>(p, stream) : launch_power<POWER_MODE, 32, 8>(p, stream);
   }
   return mel ? launch_mel<POWER_MODE, G, -1>(p, stream) : launch_power<POWER_MODE, G, -1>(p, stream);
@@ -1640,8 +1721,10 @@ static int launch_eo(const Pow2Params& p, const float2* tw_eo, bool mel, cudaStr
 
 int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, const float* wave, int64_t rows,
                       int64_t length, int64_t row_stride, int64_t frames, float* out, float* group_max,
-                      int64_t rows_per_group, cudaStream_t stream) {
+                      int64_t rows_per_group, cudaStream_t stream, const b200a_kaldi_desc* kd) {
   if (!pow2_applicable(*d) || stage == B200A_STAGE_COMPLEX) return B200A_EUNSUPPORTED;
+  // Kaldi features: the mel stage of n_fft <= 1024 (fbank / mfcc); spectrogram and the rest take the generic kernel
+  if (kd != nullptr && (stage != B200A_STAGE_MEL || d->n_fft > 1024)) return B200A_EUNSUPPORTED;
   if (stage >= B200A_STAGE_MEL && mel_tiles(d->n_mels) > kMaxItems) return B200A_EUNSUPPORTED;  // > 512 filters
   const WsLayout l = ws_layout(*d);
   const Pow2Extra e = pow2_layout(*d, l.total);
@@ -1686,6 +1769,30 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
               d->n_fft + (frames_per_unit - 1) * (int64_t)d->hop <= stage_floats;
   p.stage_ok = d->n_fft + (frames_per_unit - 1) * (int64_t)d->hop <= stage_floats &&  // edge units gather into it
                length + 2 * (int64_t)d->pad + d->n_fft < (int64_t)1 << 31;           // with 32-bit indices
+  p.out_width = stage >= B200A_STAGE_MEL ? d->n_mels : d->n_fft / 2 + 1;
+  p.out_col0 = 0;
+  p.k_energy_col = -1;
+  int lead = half;
+  if (kd != nullptr) {
+    p.kaldi = 1;
+    p.k_off = kd->snip_edges ? 0 : kd->window_size / 2 - kd->window_shift / 2;
+    p.k_win = kd->window_size;
+    p.k_dc = kd->remove_dc_offset;
+    p.k_preemph = kd->preemphasis;
+    p.k_energy_mode = kd->energy_col >= 0 ? kd->energy_mode : 0;
+    p.k_energy_floor = kd->energy_floor;
+    p.k_energy_col = kd->energy_col;
+    p.k_log = kd->use_log;
+    p.out_width = kd->out_width;
+    p.out_col0 = kd->out_col0;
+    p.pad_mode = kPadSymmetric;  // only reached when snip_edges == 0 (frames never leave the signal otherwise)
+    lead = p.k_off;
+    if (!p.stage_ok) return B200A_EUNSUPPORTED;  // the conditioning reads the staged span
+    p.bulk_ok = d->hop % 4 == 0 && lead % 4 == 0 && row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(wave) & 15) == 0;
+  }
+  p.out_vec = (p.out_width % 4 == 0 && p.out_col0 % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)   ? 4
+              : (p.out_width % 2 == 0 && p.out_col0 % 2 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) ? 2
+                                                                                                              : 1;
   const bool mel = stage >= B200A_STAGE_MEL;
   if (eo) {
     p.bulk_ok = d->hop % 4 == 0 && (half + d->pad) % 4 == 0 && row_stride % 4 == 0 &&
