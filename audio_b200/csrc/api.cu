@@ -9,6 +9,8 @@ int frontend_prepare_impl(const b200a_frontend_desc*, const float*, const float*
 int frontend_run_generic(const b200a_frontend_desc*, const void*, int, const float*, int64_t, int64_t, int64_t, int64_t,
                          float*, float*, int64_t, cudaStream_t, const b200a_kaldi_desc* = nullptr);
 int subtract_column_mean_impl(float*, int64_t, int64_t, int64_t, cudaStream_t);
+int istft_run_impl(const b200a_frontend_desc*, const void*, const float*, int64_t, int64_t, int64_t, int64_t, int64_t, float*,
+                   float*, int64_t, int64_t, int64_t, cudaStream_t);
 int frontend_run_pow2(const b200a_frontend_desc*, const void*, int, const float*, int64_t, int64_t, int64_t, int64_t,
                       float*, float*, int64_t, cudaStream_t,
                       const b200a_kaldi_desc* = nullptr);  // returns B200A_EUNSUPPORTED when not applicable
@@ -149,6 +151,19 @@ int b200a_amplitude_to_db(const float* x, int64_t groups, int64_t group_elems, f
   if (x == nullptr || out == nullptr || groups < 0 || group_elems < 0) return B200A_EINVAL;
   return amplitude_to_db_impl(x, groups, group_elems, multiplier, amin, offset, top_db, scratch, out,
                               static_cast<cudaStream_t>(stream));
+}
+
+int b200a_istft_run(const b200a_frontend_desc* desc, const void* workspace, const float* spec, int64_t rows,
+                    int64_t frames, int64_t stride_row, int64_t stride_bin, int64_t stride_frame, float* frame_buf,
+                    float* out, int64_t out_row_stride, int64_t start, int64_t out_len, b200a_stream stream) {
+  int rc = validate_desc(desc);
+  if (rc != B200A_OK) return rc;
+  if (!desc->onesided || desc->n_fft % 2 != 0) return B200A_EUNSUPPORTED;
+  if (rows < 0 || frames < 1 || out_len < 0 || start < 0 || out_row_stride < out_len) return B200A_EINVAL;
+  if (rows == 0 || out_len == 0) return B200A_OK;
+  if (workspace == nullptr || spec == nullptr || frame_buf == nullptr || out == nullptr) return B200A_EINVAL;
+  return istft_run_impl(desc, workspace, spec, rows, frames, stride_row, stride_bin, stride_frame, frame_buf, out,
+                        out_row_stride, start, out_len, static_cast<cudaStream_t>(stream));
 }
 
 int64_t b200a_kaldi_num_frames(int64_t length, int32_t window_size, int32_t window_shift, int32_t snip_edges) {

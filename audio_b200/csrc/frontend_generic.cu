@@ -562,6 +562,158 @@ int frontend_run_generic(const b200a_frontend_desc* d, const void* ws, int stage
   return launch_status();
 }
 
+// ------------------------------------------------------------------------------------------
+// inverse STFT (torch.istft as called by F.inverse_spectrogram, functional/functional.py:198-218)
+// ------------------------------------------------------------------------------------------
+struct IstftParams {
+  const float2* spec;  // logical [rows][n_bins][frames] complex64, element strides below
+  int64_t stride_row, stride_bin, stride_frame;
+  int64_t frames, tiles_per_row;
+  float* frame_buf;  // [rows][frames][n_fft] windowed time frames
+  const float* window;
+  const float2* twiddle;
+  const WsHeader* hdr;
+  int n_fft, pairs, n_stages;
+  int radix[kMaxStages];
+};
+
+// One CTA = 2*pairs frames of one row: Z = A + i B from the two Hermitian spectra, inverse FFT as
+// conj(FFT(conj Z)) / n_fft with the forward Stockham stages, a = Re z, b = Im z, times the window and the
+// inverse of the forward normalisation.  C2R semantics: the imaginary parts of bins 0 and n_fft/2 are ignored.
+__global__ void __launch_bounds__(256) istft_frames_kernel(const IstftParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = p.n_fft, pairs = p.pairs, n_bins = N / 2 + 1;
+  float2* buf0 = reinterpret_cast<float2*>(smem_raw);
+  float2* buf1 = buf0 + (size_t)pairs * N;
+  float2* tw = buf1 + (size_t)pairs * N;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int64_t row = blockIdx.x / p.tiles_per_row;
+  const int64_t tile = blockIdx.x - row * p.tiles_per_row;
+  const int64_t t0 = tile * (2 * pairs);
+  const float2* __restrict__ sp = p.spec + row * p.stride_row;
+  for (int i = tid; i < N; i += nthr) tw[i] = p.twiddle[i];
+  // conj(Z[k]), Z[k] = A[k] + i B[k]; for k > N/2 the Hermitian mirror conj(A[N-k]) + i conj(B[N-k])
+  for (int o = tid; o < pairs * N; o += nthr) {
+    const int pr = o / N, k = o - pr * N;
+    const int kk = k < n_bins ? k : N - k;
+    const int64_t ta = t0 + 2 * pr, tb = ta + 1;
+    float2 a = make_float2(0.f, 0.f), b = a;
+    if (ta < p.frames) a = sp[kk * p.stride_bin + ta * p.stride_frame];
+    if (tb < p.frames) b = sp[kk * p.stride_bin + tb * p.stride_frame];
+    if (kk == 0 || 2 * kk == N) a.y = b.y = 0.f;
+    if (k >= n_bins) {
+      a.y = -a.y;
+      b.y = -b.y;
+    }
+    // Z = (a.x - b.y) + i (a.y + b.x); store its conjugate
+    buf0[o] = make_float2(a.x - b.y, -(a.y + b.x));
+  }
+  __syncthreads();
+  float2* src = buf0;
+  float2* dst = buf1;
+  int Ns = 1;
+  for (int st = 0; st < p.n_stages; ++st) {
+    const int R = p.radix[st];
+    const int span = Ns * R;
+    const int NR = N / R;
+    const int step_stage = N / span, step_dft = NR;
+    for (int o = tid; o < pairs * N; o += nthr) {
+      const int pr = o / N, i = o - pr * N;
+      const int blk = i / span, rem = i - blk * span;
+      const int q = rem / Ns, k = rem - q * Ns;
+      const float2* in = src + (size_t)pr * N + blk * Ns + k;
+      const int e1 = (k * step_stage + q * step_dft) % N;
+      float2 acc = in[0];
+      int e = e1;
+      for (int r = 1; r < R; ++r) {
+        const float2 v = in[(size_t)r * NR];
+        const float2 w = tw[e];
+        acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
+        acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
+        e += e1;
+        if (e >= N) e -= N;
+      }
+      dst[o] = acc;
+    }
+    __syncthreads();
+    float2* t = src;
+    src = dst;
+    dst = t;
+    Ns = span;
+  }
+  const float gain = 1.f / ((float)N * p.hdr->scale);
+  for (int o = tid; o < pairs * N; o += nthr) {
+    const int pr = o / N, n = o - pr * N;
+    const float2 z = src[o];  // FFT(conj Z): Re z = N a[n], Im z = -N b[n]
+    const float w = p.window[n] * gain;
+    const int64_t ta = t0 + 2 * pr, tb = ta + 1;
+    if (ta < p.frames) p.frame_buf[((row * p.frames + ta) * N) + n] = z.x * w;
+    if (tb < p.frames) p.frame_buf[((row * p.frames + tb) * N) + n] = -z.y * w;
+  }
+}
+
+// Overlap-add and window-envelope normalisation: y[s'] = sum_t F[t][s - t hop] / sum_t w^2[s - t hop], s = s' + start,
+// frames added in ascending t (deterministic).  Positions beyond the last frame are zero (torch pads, :warns).
+__global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ frame_buf, const float* __restrict__ window,
+                                                        int n_fft, int hop, int64_t frames, int64_t start, int64_t out_len,
+                                                        float* __restrict__ out, int64_t out_row_stride) {
+  const int64_t row = blockIdx.y;
+  const int64_t sp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sp >= out_len) return;
+  const int64_t s = sp + start;
+  int64_t t_lo = s - n_fft + 1 <= 0 ? 0 : (s - n_fft + hop) / hop;  // ceil((s - n_fft + 1) / hop)
+  int64_t t_hi = s / hop;
+  if (t_hi > frames - 1) t_hi = frames - 1;
+  const float* fb = frame_buf + row * frames * n_fft;
+  float acc = 0.f, env = 0.f;
+  for (int64_t t = t_lo; t <= t_hi; ++t) {
+    const int n = (int)(s - t * hop);
+    const float w = window[n];
+    acc += fb[t * n_fft + n];
+    env = fmaf(w, w, env);
+  }
+  out[row * out_row_stride + sp] = t_hi >= t_lo ? acc / env : 0.f;
+}
+
+int istft_run_impl(const b200a_frontend_desc* d, const void* ws, const float* spec, int64_t rows, int64_t frames,
+                   int64_t stride_row, int64_t stride_bin, int64_t stride_frame, float* frame_buf, float* out,
+                   int64_t out_row_stride, int64_t start, int64_t out_len, cudaStream_t stream) {
+  const WsLayout l = ws_layout(*d);
+  const unsigned char* base = static_cast<const unsigned char*>(ws);
+  IstftParams p{};
+  p.n_stages = factorize(d->n_fft, p.radix);
+  if (p.n_stages < 0) return B200A_EUNSUPPORTED;
+  p.spec = reinterpret_cast<const float2*>(spec);
+  p.stride_row = stride_row;
+  p.stride_bin = stride_bin;
+  p.stride_frame = stride_frame;
+  p.frames = frames;
+  p.frame_buf = frame_buf;
+  p.window = reinterpret_cast<const float*>(base + l.window);
+  p.twiddle = reinterpret_cast<const float2*>(base + l.twiddle);
+  p.hdr = reinterpret_cast<const WsHeader*>(base + l.header);
+  p.n_fft = d->n_fft;
+  int pairs = (int)(49152 / (16 * (size_t)d->n_fft));
+  if (pairs < 1) pairs = 1;
+  if (pairs > 8) pairs = 8;
+  while (pairs > 1 && (int64_t)2 * (pairs - 1) >= frames) --pairs;
+  p.pairs = pairs;
+  p.tiles_per_row = (frames + 2 * pairs - 1) / (2 * pairs);
+  const size_t smem = sizeof(float2) * (size_t)d->n_fft * (2 * pairs + 1);
+  if (cudaFuncSetAttribute(istft_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return B200A_ECUDA;
+  const int64_t grid = rows * p.tiles_per_row;
+  if (grid <= 0 || grid > 0x7fffffffLL || rows > 65535) return B200A_EUNSUPPORTED;
+  istft_frames_kernel<<<(unsigned)grid, 256, smem, stream>>>(p);
+  int rc = launch_status();
+  if (rc != B200A_OK) return rc;
+  const int64_t blocks = (out_len + 255) / 256;
+  if (blocks > 0x7fffffffLL) return B200A_EUNSUPPORTED;
+  istft_ola_kernel<<<dim3((unsigned)blocks, (unsigned)rows), 256, 0, stream>>>(frame_buf, p.window, d->n_fft, d->hop, frames,
+                                                                               start, out_len, out, out_row_stride);
+  return launch_status();
+}
+
 int mfcc_finish_impl(const b200a_frontend_desc* d, const void* ws, const float* feat, int64_t rows,
                      int64_t frames, const float* group_max, int64_t rows_per_group, float top_db,
                      float* out, cudaStream_t stream) {

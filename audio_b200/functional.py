@@ -25,11 +25,13 @@ from ._plans import FrontendPlan, ResamplePlan, _no_autograd, _require_cuda_f32,
 
 __all__ = [
     "spectrogram",
+    "inverse_spectrogram",
     "melscale_fbanks",
     "linear_fbanks",
     "create_dct",
     "amplitude_to_DB",
     "resample",
+    "speed",
     "spectral_centroid",
     "mel_spectrogram",
     "mfcc",
@@ -82,6 +84,97 @@ def spectrogram(
     ws = plan.workspace(window, None, None)
     stage = _lib.STAGE_COMPLEX if power is None else _lib.STAGE_POWER
     return _unpack(plan.run(ws, stage, waveform), waveform)
+
+
+# ---- inverse spectrogram ------------------------------------------------------------------------------------
+_ENVELOPE_OK = {}
+
+
+def _check_window_envelope(window: Tensor, n_fft: int, win_length: int, hop: int, frames: int, start: int, end: int) -> None:
+    """torch.istft refuses windows whose overlap-added square dips below 1e-11 inside the returned range
+    ("window overlap add min"); it finds out with a device synchronisation, and so does this check -- once per
+    (window contents, geometry), cached."""
+    key = (window.data_ptr(), window._version, str(window.device), n_fft, win_length, hop, frames, start, end)
+    if key in _ENVELOPE_OK:
+        return
+    import numpy as np
+
+    w = np.zeros(n_fft, dtype=np.float64)
+    left = (n_fft - win_length) // 2
+    w[left:left + win_length] = window.detach().double().cpu().numpy()
+    expected = n_fft + hop * (frames - 1)
+    env = np.zeros(expected)
+    for t in range(frames):
+        env[t * hop:t * hop + n_fft] += w * w
+    seg = env[start:min(end, expected)]
+    if seg.size and np.abs(seg).min() < 1e-11:
+        raise RuntimeError("istft(...) window overlap add min: 1 (the window envelope is zero inside the output range)")
+    _ENVELOPE_OK[key] = True
+
+
+def inverse_spectrogram(
+    spectrogram: Tensor,
+    length: Optional[int],
+    pad: int,
+    window: Tensor,
+    n_fft: int,
+    hop_length: int,
+    win_length: int,
+    normalized: Union[bool, str],
+    center: bool = True,
+    pad_mode: str = "reflect",
+    onesided: bool = True,
+) -> Tensor:
+    """``(..., freq, time)`` complex64 -> ``(..., time)``: least-squares inverse of ``spectrogram(power=None)``
+    (reference functional.py:148-225 over ``torch.istft``).  Two kernels: Hermitian inverse FFT x window per frame pair,
+    then overlap-add with window-envelope normalisation."""
+    fl_norm, win_norm = _get_spec_norms(normalized)
+    if not spectrogram.is_complex():
+        raise ValueError("Expected `spectrogram` to be complex dtype.")
+    if not spectrogram.is_cuda:
+        raise RuntimeError(
+            f"audio_b200: spectrogram is on '{spectrogram.device}'. This package runs only hand-written sm_100a CUDA "
+            "kernels; there is no CPU or ATen fallback -- move the tensor (and the module) to a CUDA device."
+        )
+    if spectrogram.dtype != torch.complex64:
+        raise TypeError(f"audio_b200: spectrogram must be complex64 (got {spectrogram.dtype})")
+    if not onesided:
+        raise NotImplementedError("audio_b200: inverse_spectrogram(onesided=False) is not implemented")
+    _no_autograd(spectrogram)
+    shape = spectrogram.size()
+    n_bins, frames = shape[-2], shape[-1]
+    if n_bins != n_fft // 2 + 1:
+        raise RuntimeError(f"istft: expected {n_fft // 2 + 1} frequency bins for n_fft={n_fft}, got {n_bins}")
+    spec3 = spectrogram.reshape(-1, n_bins, frames)
+    rows = spec3.shape[0]
+    desc = FrontendPlan.make_desc(n_fft, win_length, hop_length, 0, center, "reflect", True, fl_norm, win_norm, 2.0)
+    plan = FrontendPlan(desc)
+    ws = plan.workspace(window, None, None)
+    expected = n_fft + hop_length * (frames - 1)
+    start = n_fft // 2 if center else 0
+    if length is not None:
+        out_len = length + 2 * pad
+    else:
+        out_len = expected - 2 * start if center else expected
+    if out_len <= 0:
+        raise RuntimeError(f"istft: the requested signal is empty (frames={frames}, n_fft={n_fft})")
+    _check_window_envelope(window, n_fft, win_length, hop_length, frames, start, start + out_len)
+    if start + out_len > expected:
+        warnings.warn("The length of signal is shorter than the length parameter. Result is being padded with zeros in "
+                      "the tail. Please check your center and hop_length settings.")
+    dev = spectrogram.device
+    real = torch.view_as_real(spec3)  # (rows, bins, frames, 2) float32 view, same storage
+    with torch.cuda.device(dev):
+        frame_buf = torch.empty((rows, frames, n_fft), dtype=torch.float32, device=dev)
+        out = torch.empty((rows, out_len), dtype=torch.float32, device=dev)
+        rc = _lib.lib().b200a_istft_run(
+            desc, ws.data_ptr(), real.data_ptr(), rows, frames, spec3.stride(0), spec3.stride(1), spec3.stride(2),
+            frame_buf.data_ptr(), out.data_ptr(), out_len, start, out_len, _stream_ptr(dev),
+        )
+    _lib.check(rc, "istft_run")
+    if length is not None and pad > 0:
+        out = out[:, pad:-pad]
+    return out.reshape(shape[:-2] + out.shape[-1:])
 
 
 def _db_groups(shape) -> int:
@@ -233,6 +326,16 @@ def resample(
         orig_freq, new_freq, gcd, lowpass_filter_width, rolloff, resampling_method, beta, waveform.device, waveform.dtype
     )
     return _apply_sinc_resample_kernel(waveform, orig_freq, new_freq, gcd, kernel, width)
+
+
+def speed(waveform: Tensor, orig_freq: int, factor: float, lengths: Optional[Tensor] = None):
+    """Adjusts waveform speed (reference functional.py:2384-2423): ``resample`` from ``int(factor * orig_freq)`` to
+    ``orig_freq``; returns ``(waveform', lengths')``."""
+    source, target = int(factor * orig_freq), int(orig_freq)
+    g = math.gcd(source, target)
+    source, target = source // g, target // g
+    out_lengths = None if lengths is None else torch.ceil(lengths * target / source).to(lengths.dtype)
+    return resample(waveform, source, target), out_lengths
 
 
 # ---- spectral centroid (SURVEY.md 8f: a weighted-sum epilogue of the same fused kernel) --------------

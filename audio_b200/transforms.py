@@ -23,7 +23,8 @@ from . import _lib
 from . import functional as F
 from ._plans import FrontendPlan, ResamplePlan
 
-__all__ = ["Spectrogram", "AmplitudeToDB", "MelScale", "MelSpectrogram", "MFCC", "LFCC", "SpectralCentroid", "Resample"]
+__all__ = ["Spectrogram", "InverseSpectrogram", "AmplitudeToDB", "MelScale", "MelSpectrogram", "MFCC", "LFCC", "SpectralCentroid", "Resample",
+           "Speed", "SpeedPerturbation"]
 
 
 class Spectrogram(torch.nn.Module):
@@ -84,6 +85,46 @@ class Spectrogram(torch.nn.Module):
         ws = self._plan.workspace(self.window, None, None)
         stage = _lib.STAGE_COMPLEX if self.power is None else _lib.STAGE_POWER
         return F._unpack(self._plan.run(ws, stage, waveform), waveform)
+
+
+class InverseSpectrogram(torch.nn.Module):
+    r"""Recover an audio signal from a complex spectrogram: ``(..., n_fft // 2 + 1, frames) -> (..., time)``.
+
+    Args are those of ``torchaudio.transforms.InverseSpectrogram`` (reference _transforms.py:126-212); buffer ``window``.
+    """
+
+    __constants__ = ["n_fft", "win_length", "hop_length", "pad", "power", "normalized"]
+
+    def __init__(
+        self,
+        n_fft: int = 400,
+        win_length: Optional[int] = None,
+        hop_length: Optional[int] = None,
+        pad: int = 0,
+        window_fn: Callable[..., Tensor] = torch.hann_window,
+        normalized: Union[bool, str] = False,
+        wkwargs: Optional[dict] = None,
+        center: bool = True,
+        pad_mode: str = "reflect",
+        onesided: bool = True,
+    ) -> None:
+        super().__init__()
+        self.n_fft = n_fft
+        self.win_length = win_length if win_length is not None else n_fft
+        self.hop_length = hop_length if hop_length is not None else self.win_length // 2
+        window = window_fn(self.win_length) if wkwargs is None else window_fn(self.win_length, **wkwargs)
+        self.register_buffer("window", window)
+        self.pad = pad
+        self.normalized = normalized
+        self.center = center
+        self.pad_mode = pad_mode
+        self.onesided = onesided
+
+    def forward(self, spectrogram: Tensor, length: Optional[int] = None) -> Tensor:
+        return F.inverse_spectrogram(
+            spectrogram, length, self.pad, self.window, self.n_fft, self.hop_length, self.win_length, self.normalized,
+            self.center, self.pad_mode, self.onesided,
+        )
 
 
 class AmplitudeToDB(torch.nn.Module):
@@ -404,3 +445,45 @@ class Resample(torch.nn.Module):
         return F._apply_sinc_resample_kernel(
             waveform, self.orig_freq, self.new_freq, self.gcd, self.kernel, self.width, self._plan
         )
+
+
+def _source_target_sample_rate(orig_freq: int, speed: float):
+    """Reduced integer rates whose ratio is the speed factor (reference _transforms.py:1951-1955)."""
+    source, target = int(speed * orig_freq), int(orig_freq)
+    g = math.gcd(source, target)
+    return source // g, target // g
+
+
+class Speed(torch.nn.Module):
+    r"""Adjusts waveform speed by resampling (reference _transforms.py:1958-2001): the waveform is treated as if
+    sampled at ``factor * orig_freq`` and brought back to ``orig_freq`` by the polyphase tensor-pipe resampler.
+
+    ``forward(waveform, lengths=None) -> (waveform', lengths')`` with ``lengths' = ceil(lengths * target / source)``.
+    """
+
+    def __init__(self, orig_freq, factor) -> None:
+        super().__init__()
+        self.orig_freq = orig_freq
+        self.factor = factor
+        self.source_sample_rate, self.target_sample_rate = _source_target_sample_rate(orig_freq, factor)
+        self.resampler = Resample(orig_freq=self.source_sample_rate, new_freq=self.target_sample_rate)
+
+    def forward(self, waveform: Tensor, lengths: Optional[Tensor] = None):
+        if lengths is None:
+            out_lengths = None
+        else:  # a handful of integers: bookkeeping, not signal processing
+            out_lengths = torch.ceil(lengths * self.target_sample_rate / self.source_sample_rate).to(lengths.dtype)
+        return self.resampler(waveform), out_lengths
+
+
+class SpeedPerturbation(torch.nn.Module):
+    r"""Speed perturbation augmentation (reference _transforms.py:2004-2055): each call draws one of ``factors``
+    uniformly (``torch.randint``, so ``torch.manual_seed`` reproduces the reference's choices) and applies ``Speed``."""
+
+    def __init__(self, orig_freq: int, factors) -> None:
+        super().__init__()
+        self.speeders = torch.nn.ModuleList([Speed(orig_freq=orig_freq, factor=factor) for factor in factors])
+
+    def forward(self, waveform: Tensor, lengths: Optional[Tensor] = None):
+        idx = int(torch.randint(len(self.speeders), ()))
+        return self.speeders[idx](waveform, lengths)

@@ -168,6 +168,23 @@ int b200a_fill_f32(float* dst, int64_t n, float value, b200a_stream stream);
  */
 int b200a_ratio_f32(const float* pairs, int64_t n, float* out, b200a_stream stream);
 
+/* ---- inverse STFT ---------------------------------------------------------------------------- */
+/*
+ * torch.istft as F.inverse_spectrogram calls it (functional/functional.py:148-225): Hermitian inverse FFT of every
+ * frame (C2R: the imaginary parts of bins 0 and n_fft/2 are ignored), x window, overlap-add, division by the
+ * overlap-added squared window, for the output positions [start, start + out_len) of the n_fft + hop*(frames-1)
+ * long signal (start = n_fft/2 when center).  The workspace is the one b200a_frontend_prepare built for the same
+ * descriptor (window, twiddles, normalisation: `normalized` modes are undone here).  onesided descriptors only.
+ *   spec      : complex64, logical [rows][n_fft/2+1][frames], strides in complex elements
+ *   frame_buf : caller-owned scratch of rows * frames * n_fft floats (the windowed time frames)
+ *   out       : [rows] signals of out_len samples, row r at out + r*out_row_stride
+ * The caller checks the window envelope (NOLA) -- torch raises when its minimum is < 1e-11; this library divides.
+ */
+int b200a_istft_run(const b200a_frontend_desc* desc, const void* workspace, const float* spec, int64_t rows,
+                    int64_t frames, int64_t stride_row, int64_t stride_bin, int64_t stride_frame,
+                    float* frame_buf, float* out, int64_t out_row_stride, int64_t start, int64_t out_len,
+                    b200a_stream stream);
+
 /* ---- Kaldi-compatible features (compliance/kaldi.py: spectrogram :229-316, fbank :514-645, mfcc :669-813) -------- */
 /*
  * Per-frame conditioning and output placement of the Kaldi front end; the transform itself (window, FFT size,

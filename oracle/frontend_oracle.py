@@ -436,3 +436,52 @@ def resample(
     g = math.gcd(int(orig_freq), int(new_freq))
     k, w = sinc_resample_kernel(orig_freq, new_freq, g, lowpass_filter_width, rolloff, resampling_method, beta)
     return apply_sinc_resample_kernel(x, orig_freq, new_freq, g, k, w)
+
+
+def istft(spec, n_fft, hop_length, win_length, window, center=True, normalized=False, length=None):
+    """torch.istft restated (ATen `istft`, the third-party arithmetic F.inverse_spectrogram calls at
+    functional.py:198-209): spec (..., n_fft//2+1, T) complex -> (..., time).
+
+    irfft of every frame (C2R: imaginary parts of bins 0 and n_fft/2 ignored; `normalized` multiplies by sqrt(n_fft)),
+    times the centre-padded window, overlap-add at hop_length, division by the overlap-added squared window, the
+    slice [n_fft/2, n_fft/2 + length) when centred (zero tail if `length` exceeds what the frames cover)."""
+    spec = np.asarray(spec, dtype=np.complex128)
+    lead = spec.shape[:-2]
+    frames = spec.shape[-1]
+    sp = spec.reshape((-1,) + spec.shape[-2:])
+    w = np.zeros(n_fft)
+    left = (n_fft - win_length) // 2
+    w[left:left + win_length] = np.asarray(window, dtype=np.float64)
+    if normalized:
+        sp = sp * math.sqrt(n_fft)
+    fr = np.fft.irfft(np.swapaxes(sp, 1, 2), n=n_fft, axis=-1) * w  # (rows, T, n_fft)
+    expected = n_fft + hop_length * (frames - 1)
+    y = np.zeros((sp.shape[0], expected))
+    env = np.zeros(expected)
+    for t in range(frames):
+        y[:, t * hop_length:t * hop_length + n_fft] += fr[:, t]
+        env[t * hop_length:t * hop_length + n_fft] += w * w
+    start = n_fft // 2 if center else 0
+    if length is not None:
+        end = start + length
+    else:
+        end = expected - n_fft // 2 if center else expected
+    seg_end = min(end, expected)
+    assert np.abs(env[start:seg_end]).min() > 1e-11, "window overlap add min"
+    out = y[:, start:seg_end] / env[start:seg_end]
+    if end > expected:
+        out = np.concatenate([out, np.zeros((out.shape[0], end - expected))], axis=1)
+    return out.reshape(lead + (out.shape[-1],))
+
+
+def inverse_spectrogram(spec, length, pad, window, n_fft, hop_length, win_length, normalized=False, center=True):
+    """reference functional.py:148-225."""
+    spec = np.asarray(spec, dtype=np.complex128)
+    frame_norm = normalized == "frame_length"
+    if normalized is True or normalized == "window":
+        spec = spec * np.sqrt((np.asarray(window, dtype=np.float64) ** 2).sum())
+    y = istft(spec, n_fft, hop_length, win_length, window, center=center, normalized=frame_norm,
+              length=length + 2 * pad if length is not None else None)
+    if length is not None and pad > 0:
+        y = y[..., pad:-pad]
+    return y

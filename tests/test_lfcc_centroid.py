@@ -85,3 +85,35 @@ def test_gpu_lfcc_and_centroid_reference(ref_cases):
     got = T.SpectralCentroid(16000).cuda()(x.reshape(2, 2, -1))
     assert tuple(got.shape) == (2, 2, 81)
     assert_close(got.reshape(4, 81).cpu().numpy(), ref_cases["centroid_default_out"], rtol=2e-5, atol=2e-2)
+
+
+def test_speed_surface_cpu():
+    import audio_b200.transforms as T
+
+    sp = T.Speed(16000, 1.1)
+    assert (sp.source_sample_rate, sp.target_sample_rate) == (11, 10)
+    assert (sp.resampler.orig_freq, sp.resampler.new_freq) == (11, 10)
+    assert (T.Speed(44100, 0.9).source_sample_rate, T.Speed(44100, 0.9).target_sample_rate) == (9, 10)
+    pert = T.SpeedPerturbation(16000, [0.9, 1.1, 1.0])
+    assert len(pert.speeders) == 3
+
+
+@pytest.mark.gpu
+def test_gpu_speed_matches_oracle_resample():
+    import audio_b200.functional as F
+    import audio_b200.transforms as T
+
+    x = torch.randn(3, 8000, generator=torch.Generator().manual_seed(3))
+    lengths = torch.tensor([8000, 4001, 17])
+    for factor, (src, dst) in ((1.1, (11, 10)), (0.9, (9, 10))):
+        y, out_len = T.Speed(16000, factor).cuda()(x.cuda(), lengths.cuda())
+        exp = O.resample(x.numpy(), src, dst)
+        assert tuple(y.shape) == exp.shape
+        assert np.abs(y.cpu().numpy() - exp).max() <= 1e-4 * np.abs(exp).max()
+        assert out_len.cpu().tolist() == [int(np.ceil(n * dst / src)) for n in lengths.tolist()]
+        y2, none = F.speed(x.cuda(), 16000, factor)
+        assert none is None and np.abs(y2.cpu().numpy() - exp).max() <= 1e-4 * np.abs(exp).max()
+    torch.manual_seed(0)
+    pert = T.SpeedPerturbation(16000, [0.9, 1.1, 1.0]).cuda()
+    y, _ = pert(x.cuda())
+    assert y.shape[-1] in (8889, 7273, 8000)
