@@ -98,6 +98,11 @@ _SIGNATURES = {
         [POINTER(FrontendDesc), c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
          c_int64, c_int64, c_void_p],
     ),
+    "b200a_griffinlim_update": (
+        ctypes.c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_float, c_int32, c_void_p, c_int64, c_int64, c_int64,
+         c_void_p],
+    ),
     "b200a_kaldi_num_frames": (c_int64, [c_int64, c_int32, c_int32, c_int32]),
     "b200a_kaldi_run": (
         ctypes.c_int,

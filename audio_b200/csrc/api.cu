@@ -9,6 +9,8 @@ int frontend_prepare_impl(const b200a_frontend_desc*, const float*, const float*
 int frontend_run_generic(const b200a_frontend_desc*, const void*, int, const float*, int64_t, int64_t, int64_t, int64_t,
                          float*, float*, int64_t, cudaStream_t, const b200a_kaldi_desc* = nullptr);
 int subtract_column_mean_impl(float*, int64_t, int64_t, int64_t, cudaStream_t);
+int griffinlim_update_impl(const float*, int64_t, int64_t, int64_t, float, const float*, const float*, float, int, float*,
+                           int64_t, int64_t, int64_t, cudaStream_t);
 int istft_run_impl(const b200a_frontend_desc*, const void*, const float*, int64_t, int64_t, int64_t, int64_t, int64_t, float*,
                    float*, int64_t, int64_t, int64_t, cudaStream_t);
 int frontend_run_pow2(const b200a_frontend_desc*, const void*, int, const float*, int64_t, int64_t, int64_t, int64_t,
@@ -164,6 +166,16 @@ int b200a_istft_run(const b200a_frontend_desc* desc, const void* workspace, cons
   if (workspace == nullptr || spec == nullptr || frame_buf == nullptr || out == nullptr) return B200A_EINVAL;
   return istft_run_impl(desc, workspace, spec, rows, frames, stride_row, stride_bin, stride_frame, frame_buf, out,
                         out_row_stride, start, out_len, static_cast<cudaStream_t>(stream));
+}
+
+int b200a_griffinlim_update(const float* mag, int64_t stride_row, int64_t stride_bin, int64_t stride_frame, float inv_power,
+                            const float* rebuilt, const float* tprev, float momentum, int32_t normalize, float* proj,
+                            int64_t rows, int64_t bins, int64_t frames, b200a_stream stream) {
+  if (rows < 0 || bins < 1 || frames < 1 || !(inv_power > 0.f)) return B200A_EINVAL;
+  if (rows == 0) return B200A_OK;
+  if (mag == nullptr || proj == nullptr || (tprev != nullptr && rebuilt == nullptr)) return B200A_EINVAL;
+  return griffinlim_update_impl(mag, stride_row, stride_bin, stride_frame, inv_power, rebuilt, tprev, momentum, normalize,
+                                proj, rows, bins, frames, static_cast<cudaStream_t>(stream));
 }
 
 int64_t b200a_kaldi_num_frames(int64_t length, int32_t window_size, int32_t window_shift, int32_t snip_edges) {

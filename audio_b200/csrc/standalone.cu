@@ -134,4 +134,46 @@ int subtract_column_mean_impl(float* x, int64_t rows, int64_t frames, int64_t wi
   return launch_status();
 }
 
+// Griffin-Lim phase step (functional.py:330-341): proj = mag^(1/power) * angles,
+//   angles = d / (|d| + 1e-16), d = rebuilt - momentum * tprev   (angles = 1 when there is no rebuilt yet).
+// mag: logical [rows][bins][frames] with element strides; rebuilt / tprev / proj: frame-major [rows][frames][bins] complex.
+__global__ void __launch_bounds__(256) griffinlim_update_kernel(const float* __restrict__ mag, int64_t ms_row, int64_t ms_bin,
+                                                                int64_t ms_frame, float inv_power,
+                                                                const float2* __restrict__ rebuilt,
+                                                                const float2* __restrict__ tprev, float momentum, int normalize,
+                                                                float2* __restrict__ proj, int64_t bins, int64_t frames,
+                                                                int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i % bins, rt = i / bins;
+    const int64_t t = rt % frames, r = rt / frames;
+    float m = mag[r * ms_row + k * ms_bin + t * ms_frame];
+    m = inv_power == 1.f ? m : (inv_power == 0.5f ? sqrtf(m) : powf(m, inv_power));
+    float2 a = make_float2(1.f, 0.f);
+    if (rebuilt != nullptr) {
+      float2 d = rebuilt[i];
+      if (tprev != nullptr) {
+        const float2 p = tprev[i];
+        d.x -= momentum * p.x;
+        d.y -= momentum * p.y;
+      }
+      const float inv = normalize ? 1.f / (hypotf(d.x, d.y) + 1e-16f) : 1.f;
+      a = make_float2(d.x * inv, d.y * inv);
+    }
+    proj[i] = make_float2(m * a.x, m * a.y);
+  }
+}
+
+int griffinlim_update_impl(const float* mag, int64_t ms_row, int64_t ms_bin, int64_t ms_frame, float inv_power,
+                           const float* rebuilt, const float* tprev, float momentum, int normalize, float* proj,
+                           int64_t rows, int64_t bins, int64_t frames, cudaStream_t stream) {
+  const int64_t total = rows * bins * frames;
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  griffinlim_update_kernel<<<(unsigned)grid, 256, 0, stream>>>(mag, ms_row, ms_bin, ms_frame, inv_power,
+                                                              reinterpret_cast<const float2*>(rebuilt),
+                                                              reinterpret_cast<const float2*>(tprev), momentum, normalize,
+                                                              reinterpret_cast<float2*>(proj), bins, frames, total);
+  return launch_status();
+}
+
 }  // namespace b200a

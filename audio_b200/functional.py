@@ -26,6 +26,7 @@ from ._plans import FrontendPlan, ResamplePlan, _no_autograd, _require_cuda_f32,
 __all__ = [
     "spectrogram",
     "inverse_spectrogram",
+    "griffinlim",
     "melscale_fbanks",
     "linear_fbanks",
     "create_dct",
@@ -175,6 +176,80 @@ def inverse_spectrogram(
     if length is not None and pad > 0:
         out = out[:, pad:-pad]
     return out.reshape(shape[:-2] + out.shape[-1:])
+
+
+def griffinlim(
+    specgram: Tensor,
+    window: Tensor,
+    n_fft: int,
+    hop_length: int,
+    win_length: int,
+    power: float,
+    n_iter: int,
+    momentum: float,
+    length: Optional[int],
+    rand_init: bool,
+) -> Tensor:
+    """Fast Griffin-Lim phase recovery: ``(..., freq, time)`` |X|^power -> ``(..., time)`` (reference
+    functional.py:255-353).  Every iteration is four launches on device-resident buffers: the phase step
+    (``b200a_griffinlim_update``), the two inverse-STFT kernels, and the fused forward STFT (complex stage)."""
+    if not 0 <= momentum < 1:
+        raise ValueError("momentum must be in range [0, 1). Found: {}".format(momentum))
+    momentum = momentum / (1 + momentum)
+    _require_cuda_f32(specgram, "specgram")
+    _no_autograd(specgram)
+    shape = specgram.size()
+    n_bins, frames = shape[-2], shape[-1]
+    spec3 = specgram.reshape(-1, n_bins, frames)
+    rows = spec3.shape[0]
+    dev = specgram.device
+    desc = FrontendPlan.make_desc(n_fft, win_length, hop_length, 0, True, "reflect", True, False, False, None)
+    plan = FrontendPlan(desc)
+    ws = plan.workspace(window, None, None)
+    expected = n_fft + hop_length * (frames - 1)
+    start = n_fft // 2
+    out_len = length if length is not None else expected - 2 * start
+    _check_window_envelope(window, n_fft, win_length, hop_length, frames, start, start + out_len)
+    lib = _lib.lib()
+    stream = _stream_ptr(dev)
+    with torch.cuda.device(dev):
+        proj = torch.empty((rows, frames, n_bins, 2), dtype=torch.float32, device=dev)
+        frame_buf = torch.empty((rows, frames, n_fft), dtype=torch.float32, device=dev)
+        wave = torch.empty((rows, out_len), dtype=torch.float32, device=dev)
+        rebuilt, tprev = None, None
+        first_raw = False
+        if rand_init:
+            # the reference's own call (functional.py:310-311): uniform real and imaginary parts from torch's generator
+            # on this device, in the (rows, freq, time) element order; used un-normalised for the first inversion
+            init = torch.rand(spec3.size(), dtype=torch.complex64, device=dev)
+            rebuilt = torch.view_as_real(init.transpose(1, 2).contiguous())
+            first_raw = True
+
+        def invert():
+            rc = lib.b200a_istft_run(desc, ws.data_ptr(), proj.data_ptr(), rows, frames, frames * n_bins, 1, n_bins,
+                                     frame_buf.data_ptr(), wave.data_ptr(), out_len, start, out_len, stream)
+            _lib.check(rc, "istft_run")
+
+        def step(raw=False):
+            rc = lib.b200a_griffinlim_update(
+                spec3.data_ptr(), spec3.stride(0), spec3.stride(1), spec3.stride(2), 1.0 / float(power),
+                None if rebuilt is None else rebuilt.data_ptr(), None if tprev is None or not momentum else tprev.data_ptr(),
+                float(momentum), 0 if raw else 1, proj.data_ptr(), rows, n_bins, frames, stream)
+            _lib.check(rc, "griffinlim_update")
+
+        for it in range(n_iter):
+            step(raw=first_raw and it == 0)
+            invert()
+            new = plan.run(ws, _lib.STAGE_COMPLEX, wave)  # (rows, T', bins, 2) frame-major
+            if new.shape[1] != frames:
+                raise RuntimeError(
+                    f"griffinlim: the rebuilt spectrogram has {new.shape[1]} frames, the input {frames} "
+                    "(`length` is inconsistent with hop_length and the number of frames)"
+                )
+            tprev, rebuilt = (None if (first_raw and it == 0) else rebuilt), new
+        step(raw=first_raw and n_iter == 0)
+        invert()
+    return wave.reshape(shape[:-2] + wave.shape[-1:])
 
 
 def _db_groups(shape) -> int:

@@ -23,7 +23,7 @@ from . import _lib
 from . import functional as F
 from ._plans import FrontendPlan, ResamplePlan
 
-__all__ = ["Spectrogram", "InverseSpectrogram", "AmplitudeToDB", "MelScale", "MelSpectrogram", "MFCC", "LFCC", "SpectralCentroid", "Resample",
+__all__ = ["Spectrogram", "InverseSpectrogram", "GriffinLim", "AmplitudeToDB", "MelScale", "MelSpectrogram", "MFCC", "LFCC", "SpectralCentroid", "Resample",
            "Speed", "SpeedPerturbation"]
 
 
@@ -124,6 +124,46 @@ class InverseSpectrogram(torch.nn.Module):
         return F.inverse_spectrogram(
             spectrogram, length, self.pad, self.window, self.n_fft, self.hop_length, self.win_length, self.normalized,
             self.center, self.pad_mode, self.onesided,
+        )
+
+
+class GriffinLim(torch.nn.Module):
+    r"""Compute a waveform from a linear-scale magnitude spectrogram with the fast Griffin-Lim transformation
+    (reference _transforms.py:215-297): ``(..., n_fft // 2 + 1, frames) -> (..., time)``; buffer ``window``."""
+
+    __constants__ = ["n_fft", "n_iter", "win_length", "hop_length", "power", "length", "momentum", "rand_init"]
+
+    def __init__(
+        self,
+        n_fft: int = 400,
+        n_iter: int = 32,
+        win_length: Optional[int] = None,
+        hop_length: Optional[int] = None,
+        window_fn: Callable[..., Tensor] = torch.hann_window,
+        power: float = 2.0,
+        wkwargs: Optional[dict] = None,
+        momentum: float = 0.99,
+        length: Optional[int] = None,
+        rand_init: bool = True,
+    ) -> None:
+        super().__init__()
+        if not (0 <= momentum < 1):
+            raise ValueError("momentum must be in the range [0, 1). Found: {}".format(momentum))
+        self.n_fft = n_fft
+        self.n_iter = n_iter
+        self.win_length = win_length if win_length is not None else n_fft
+        self.hop_length = hop_length if hop_length is not None else self.win_length // 2
+        window = window_fn(self.win_length) if wkwargs is None else window_fn(self.win_length, **wkwargs)
+        self.register_buffer("window", window)
+        self.length = length
+        self.power = power
+        self.momentum = momentum
+        self.rand_init = rand_init
+
+    def forward(self, specgram: Tensor) -> Tensor:
+        return F.griffinlim(
+            specgram, self.window, self.n_fft, self.hop_length, self.win_length, self.power, self.n_iter, self.momentum,
+            self.length, self.rand_init,
         )
 
 

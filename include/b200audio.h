@@ -185,6 +185,20 @@ int b200a_istft_run(const b200a_frontend_desc* desc, const void* workspace, cons
                     float* frame_buf, float* out, int64_t out_row_stride, int64_t start, int64_t out_len,
                     b200a_stream stream);
 
+/*
+ * One phase step of F.griffinlim (functional/functional.py:330-341):
+ *   proj = mag^inv_power * angles,  angles = d / (|d| + 1e-16),  d = rebuilt - momentum * tprev
+ * with angles = 1 when rebuilt is NULL (the first inversion, rand_init = False), d = rebuilt when tprev is NULL, and
+ * angles = rebuilt as is when normalize == 0 (the first inversion with a random initial phase, :310-311).
+ *   mag                   : |X|^power, logical [rows][bins][frames] with element strides (the user's tensor)
+ *   rebuilt, tprev, proj  : complex64 frame-major [rows][frames][bins] (what b200a_frontend_run(COMPLEX) writes and
+ *                           b200a_istft_run reads with strides (frames*bins, 1, bins))
+ */
+int b200a_griffinlim_update(const float* mag, int64_t stride_row, int64_t stride_bin, int64_t stride_frame,
+                            float inv_power, const float* rebuilt, const float* tprev, float momentum,
+                            int32_t normalize, float* proj, int64_t rows, int64_t bins, int64_t frames,
+                            b200a_stream stream);
+
 /* ---- Kaldi-compatible features (compliance/kaldi.py: spectrogram :229-316, fbank :514-645, mfcc :669-813) -------- */
 /*
  * Per-frame conditioning and output placement of the Kaldi front end; the transform itself (window, FFT size,

@@ -485,3 +485,28 @@ def inverse_spectrogram(spec, length, pad, window, n_fft, hop_length, win_length
     if length is not None and pad > 0:
         y = y[..., pad:-pad]
     return y
+
+
+def griffinlim(specgram, window, n_fft, hop_length, win_length, power, n_iter, momentum, length):
+    """reference functional.py:255-353 with rand_init=False: fast Griffin-Lim phase recovery.
+
+    specgram (..., freq, time) holds |X|^power; every iteration inverts the current estimate (istft), rebuilds its STFT
+    (centred, reflect), and keeps only the phase of `rebuilt - m/(1+m) * previous rebuilt`."""
+    if not 0 <= momentum < 1:
+        raise ValueError("momentum must be in range [0, 1). Found: {}".format(momentum))
+    momentum = momentum / (1 + momentum)
+    spec = np.asarray(specgram, dtype=np.float64)
+    lead = spec.shape[:-2]
+    mag = spec.reshape((-1,) + spec.shape[-2:]) ** (1.0 / power)
+    angles = np.ones(mag.shape, dtype=np.complex128)
+    tprev = 0.0
+    for _ in range(n_iter):
+        inverse = istft(mag * angles, n_fft, hop_length, win_length, window, length=length)
+        rebuilt = stft(inverse, n_fft, hop_length, window, center=True, pad_mode="reflect")
+        angles = rebuilt
+        if momentum:
+            angles = angles - tprev * momentum
+        angles = angles / (np.abs(angles) + 1e-16)
+        tprev = rebuilt
+    out = istft(mag * angles, n_fft, hop_length, win_length, window, length=length)
+    return out.reshape(lead + out.shape[-1:])

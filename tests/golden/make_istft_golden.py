@@ -45,5 +45,39 @@ def main():
     np.savez_compressed(os.path.join(HERE, "istft_ref_cases.npz"), **out)
 
 
+def griffinlim_goldens():
+    """The two librosa.griffinlim outputs the reference's test holds (functional/librosa_compatibility_test_impl.py:16-54,
+    float64, n_fft 400 / hop 100 / power 1 / 8 iterations, momentum 0 and 0.99, atol 5e-5) with the magnitude
+    spectrogram they were computed from (get_whitenoise -> get_spectrogram, common_utils/data_utils.py)."""
+    import importlib.util
+
+    spec_ = importlib.util.spec_from_file_location(
+        "ref_data_utils", os.path.join(REF, "test/torchaudio_unittest/common_utils/data_utils.py"))
+    du = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(du)
+    assets = os.path.join(REF, "test/torchaudio_unittest/assets/librosa_expected_results/test/torchaudio_unittest/functional")
+    wave = du.get_whitenoise(dtype=torch.float64)
+    window = torch.hann_window(400)
+    specgram = du.get_spectrogram(wave, n_fft=400, hop_length=100, power=1, win_length=400, window=window)
+    out = {"waveform": wave.numpy(), "specgram": specgram.numpy()}
+    for tag in ("0", "0_99"):
+        t = torch.load(os.path.join(assets, f"librosa_compatibility_test.py__TestFunctionalCPU__test_griffinlim_{tag}.pt"),
+                       weights_only=False)
+        out[f"librosa_{tag}"] = np.asarray(t)
+        res = F.griffinlim(specgram, window=window.double(), n_fft=400, hop_length=100, win_length=400, power=1, n_iter=8,
+                           momentum=float(tag.replace("_", ".")), length=wave.size(1), rand_init=False)
+        out[f"ref_{tag}"] = res.numpy()
+    # a float32 run of the reference with the module defaults (power 2, 32 iterations, momentum 0.99)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 6000, generator=g)
+    w = torch.hann_window(512)
+    p2 = F.spectrogram(x, 0, w, 512, 128, 512, 2.0, False)
+    out["power_spec_512"] = p2.numpy()
+    out["ref_512"] = F.griffinlim(p2, w, 512, 128, 512, 2.0, 32, 0.99, 6000, False).numpy()
+    np.savez_compressed(os.path.join(HERE, "griffinlim_goldens.npz"), **out)
+    print("griffinlim_goldens.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     main()
+    griffinlim_goldens()

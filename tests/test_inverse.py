@@ -113,3 +113,71 @@ def test_gpu_round_trip(n_fft, hop, win):
     assert (y - x).abs().max().item() < 2e-5
     with pytest.raises(RuntimeError, match="window overlap add min"):
         T.InverseSpectrogram(n_fft=n_fft, hop_length=win, win_length=win // 2).cuda()(fwd(x)[..., :5], None)
+
+
+# ---- Griffin-Lim --------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gl_goldens():
+    return np.load(os.path.join(GOLDEN, "griffinlim_goldens.npz"))
+
+
+@pytest.mark.parametrize("tag,momentum", [("0", 0.0), ("0_99", 0.99)])
+def test_oracle_griffinlim_matches_librosa(gl_goldens, tag, momentum):
+    """The reference's own golden test (functional/librosa_compatibility_test_impl.py:16-54): float64, atol 5e-5."""
+    got = O.griffinlim(gl_goldens["specgram"], O.hann_window(400), 400, 100, 400, 1, 8, momentum, 16000)
+    np.testing.assert_allclose(got[0], gl_goldens[f"librosa_{tag}"], atol=5e-5, rtol=1e-7)
+    assert np.abs(got - gl_goldens[f"ref_{tag}"]).max() < 1e-4  # the reference ran with a float32-built window
+
+
+def test_griffinlim_surface_cpu():
+    import audio_b200.transforms as T
+
+    gl = T.GriffinLim()
+    assert (gl.n_fft, gl.n_iter, gl.win_length, gl.hop_length, gl.power, gl.momentum, gl.length, gl.rand_init) == (
+        400, 32, 400, 200, 2.0, 0.99, None, True)
+    with pytest.raises(ValueError, match="momentum must be in the range"):
+        T.GriffinLim(momentum=1.0)
+    import audio_b200.functional as F
+
+    with pytest.raises(ValueError, match="momentum must be in range"):
+        F.griffinlim(torch.zeros(1, 201, 10), torch.hann_window(400), 400, 100, 400, 1, 8, 1.5, None, False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,momentum", [("0", 0.0), ("0_99", 0.99)])
+def test_gpu_griffinlim_matches_librosa(gl_goldens, tag, momentum):
+    """Same case in float32 on the GPU: 8 iterations of istft / stft round-off stay within 1e-3 of the float64 golden
+    (signal amplitude ~1); the reference's float32 run sits at the same distance."""
+    import audio_b200.functional as F
+
+    spec = torch.from_numpy(gl_goldens["specgram"]).float().cuda()
+    got = F.griffinlim(spec, torch.hann_window(400).cuda(), 400, 100, 400, 1, 8, momentum, 16000, False)
+    assert tuple(got.shape) == (1, 16000)
+    assert np.abs(got.cpu().numpy()[0] - gl_goldens[f"librosa_{tag}"]).max() < 1e-3
+
+
+@pytest.mark.gpu
+def test_gpu_griffinlim_module_defaults(gl_goldens):
+    import audio_b200.transforms as T
+
+    spec = torch.from_numpy(gl_goldens["power_spec_512"]).cuda()
+    gl = T.GriffinLim(n_fft=512, hop_length=128, length=6000, rand_init=False).cuda()
+    got = gl(spec).cpu().numpy()
+    assert got.shape == (2, 6000)
+    oracle = O.griffinlim(gl_goldens["power_spec_512"], O.hann_window(512), 512, 128, 512, 2.0, 32, 0.99, 6000)
+    # 32 momentum iterations amplify float32 round-off; the reference's own float32 run differs from float64 by 2e-3
+    assert np.abs(got - oracle).max() < 2e-2 * np.abs(oracle).max()
+    assert np.abs(got - gl_goldens["ref_512"]).max() < 2e-2 * np.abs(oracle).max()
+    # the recovered signal's magnitude spectrogram is close to the target (what Griffin-Lim optimises)
+    rebuilt = T.Spectrogram(n_fft=512, hop_length=128, power=2.0).cuda()(torch.from_numpy(got).cuda())
+    rel = (rebuilt - spec).norm() / spec.norm()
+    assert rel.item() < 0.35
+    # random initial phase: runs, is reproducible under torch.manual_seed, and converges about as well
+    gl_r = T.GriffinLim(n_fft=512, hop_length=128, length=6000).cuda()
+    torch.manual_seed(1)
+    a = gl_r(spec)
+    torch.manual_seed(1)
+    b = gl_r(spec)
+    assert torch.equal(a, b)
+    rel_r = (T.Spectrogram(n_fft=512, hop_length=128, power=2.0).cuda()(a) - spec).norm() / spec.norm()
+    assert rel_r.item() < 0.35
