@@ -595,14 +595,23 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_pow2_power_kernel(const Pow2P
     transform_unit<POWER_MODE, G, HG, STAGE_IS_TILE>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa, pb);
     const int64_t ta = cur.ub * Ge::kFrames + 2 * gi;
     const bool has_a = ta < p.frames, has_b = ta + 1 < p.frames;
-    float* oa = p.out + (cur.row * p.frames + ta) * Ge::kBins;
-    float* ob = oa + Ge::kBins;
+    float* oa = p.out + (cur.row * p.frames + ta) * p.out_width + p.out_col0;
+    float* ob = oa + p.out_width;
+    if (p.k_log) {  // Kaldi spectrogram: log(max(|X|^2, eps)), kaldi.py:310
+#pragma unroll
+      for (int m = 0; m < 17; ++m) {
+        pa[m] = logf(fmaxf(pa[m], kKaldiEps));
+        pb[m] = logf(fmaxf(pb[m], kKaldiEps));
+      }
+    }
+    const int skip = p.k_energy_col - p.out_col0;  // the bin whose column holds the frame's log energy (-1: none)
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
+      if (l + G * m == skip) continue;
       if (has_a) oa[l + G * m] = pa[m];
       if (has_b) ob[l + G * m] = pb[m];
     }
-    if (l == 0) {
+    if (l == 0 && Ge::kNfft / 2 != skip) {
       if (has_a) oa[Ge::kNfft / 2] = pa[16];
       if (has_b) ob[Ge::kNfft / 2] = pb[16];
     }
@@ -1723,8 +1732,8 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
                       int64_t length, int64_t row_stride, int64_t frames, float* out, float* group_max,
                       int64_t rows_per_group, cudaStream_t stream, const b200a_kaldi_desc* kd) {
   if (!pow2_applicable(*d) || stage == B200A_STAGE_COMPLEX) return B200A_EUNSUPPORTED;
-  // Kaldi features: the mel stage of n_fft <= 1024 (fbank / mfcc); spectrogram and the rest take the generic kernel
-  if (kd != nullptr && (stage != B200A_STAGE_MEL || d->n_fft > 1024)) return B200A_EUNSUPPORTED;
+  // Kaldi features with a 256 / 512 / 1024-point FFT; every other size takes the generic kernel
+  if (kd != nullptr && d->n_fft > 1024) return B200A_EUNSUPPORTED;
   if (stage >= B200A_STAGE_MEL && mel_tiles(d->n_mels) > kMaxItems) return B200A_EUNSUPPORTED;  // > 512 filters
   const WsLayout l = ws_layout(*d);
   const Pow2Extra e = pow2_layout(*d, l.total);
