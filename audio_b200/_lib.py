@@ -103,6 +103,10 @@ _SIGNATURES = {
         [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_float, c_int32, c_void_p, c_int64, c_int64, c_int64,
          c_void_p],
     ),
+    "b200a_phase_vocoder": (
+        ctypes.c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_double, c_void_p, c_void_p, c_int64, c_void_p],
+    ),
     "b200a_kaldi_num_frames": (c_int64, [c_int64, c_int32, c_int32, c_int32]),
     "b200a_kaldi_run": (
         ctypes.c_int,

@@ -9,6 +9,8 @@ int frontend_prepare_impl(const b200a_frontend_desc*, const float*, const float*
 int frontend_run_generic(const b200a_frontend_desc*, const void*, int, const float*, int64_t, int64_t, int64_t, int64_t,
                          float*, float*, int64_t, cudaStream_t, const b200a_kaldi_desc* = nullptr);
 int subtract_column_mean_impl(float*, int64_t, int64_t, int64_t, cudaStream_t);
+int phase_vocoder_impl(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, double, const float*, float*, int64_t,
+                       cudaStream_t);
 int griffinlim_update_impl(const float*, int64_t, int64_t, int64_t, float, const float*, const float*, float, int, float*,
                            int64_t, int64_t, int64_t, cudaStream_t);
 int istft_run_impl(const b200a_frontend_desc*, const void*, const float*, int64_t, int64_t, int64_t, int64_t, int64_t, float*,
@@ -176,6 +178,16 @@ int b200a_griffinlim_update(const float* mag, int64_t stride_row, int64_t stride
   if (mag == nullptr || proj == nullptr || (tprev != nullptr && rebuilt == nullptr)) return B200A_EINVAL;
   return griffinlim_update_impl(mag, stride_row, stride_bin, stride_frame, inv_power, rebuilt, tprev, momentum, normalize,
                                 proj, rows, bins, frames, static_cast<cudaStream_t>(stream));
+}
+
+int b200a_phase_vocoder(const float* spec, int64_t stride_row, int64_t stride_bin, int64_t stride_frame, int64_t rows,
+                        int64_t bins, int64_t frames_in, double rate, const float* phase_advance, float* out,
+                        int64_t frames_out, b200a_stream stream) {
+  if (rows < 0 || bins < 1 || frames_in < 1 || frames_out < 0 || !(rate > 0.0)) return B200A_EINVAL;
+  if (rows == 0 || frames_out == 0) return B200A_OK;
+  if (spec == nullptr || phase_advance == nullptr || out == nullptr) return B200A_EINVAL;
+  return phase_vocoder_impl(spec, stride_row, stride_bin, stride_frame, rows, bins, frames_in, rate, phase_advance, out,
+                            frames_out, static_cast<cudaStream_t>(stream));
 }
 
 int64_t b200a_kaldi_num_frames(int64_t length, int32_t window_size, int32_t window_shift, int32_t snip_edges) {

@@ -176,4 +176,50 @@ int griffinlim_update_impl(const float* mag, int64_t ms_row, int64_t ms_bin, int
   return launch_status();
 }
 
+// F.phase_vocoder (functional.py:713-803): one thread per (row, bin) walks the output frames in order, carrying the
+// accumulated phase (the reference's cumsum); consecutive threads are consecutive bins of the frame-major output.
+//   time step t' sits at ts = float(rate * t') of the input; its neighbours are frames trunc(ts) and trunc(ts + 1)
+//   (frames >= frames_in are the two zero frames the reference pads); alpha = ts mod 1.
+__global__ void __launch_bounds__(128) phase_vocoder_kernel(const float2* __restrict__ spec, int64_t s_row, int64_t s_bin,
+                                                            int64_t s_frame, int64_t bins, int64_t frames_in, double rate,
+                                                            const float* __restrict__ phase_advance,
+                                                            float2* __restrict__ out, int64_t frames_out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = blockIdx.y;
+  if (k >= bins) return;
+  const float2* sp = spec + r * s_row + k * s_bin;
+  float2* o = out + r * frames_out * bins + k;
+  const float pa = phase_advance[k];
+  const float two_pi = 6.283185307179586f;
+  const float2 first = sp[0];
+  // the accumulated phase grows to thousands of radians: carried in double so that its round-off (1e-3 rad in the
+  // reference's float32 cumsum) does not reach the output
+  double acc = (double)atan2f(first.y, first.x);  // phase_0
+  for (int64_t t = 0; t < frames_out; ++t) {
+    const float ts = (float)(rate * (double)t);
+    const float alpha = fmodf(ts, 1.0f);
+    const int64_t i0 = (int64_t)ts, i1 = (int64_t)(ts + 1.0f);
+    const float2 z0 = i0 < frames_in ? sp[i0 * s_frame] : make_float2(0.f, 0.f);
+    const float2 z1 = i1 < frames_in ? sp[i1 * s_frame] : make_float2(0.f, 0.f);
+    const float n0 = hypotf(z0.x, z0.y), n1 = hypotf(z1.x, z1.y);
+    const float mag = alpha * n1 + (1.f - alpha) * n0;
+    float sn, cs;
+    sincosf((float)(acc - 6.283185307179586 * rint(acc / 6.283185307179586)), &sn, &cs);
+    o[t * bins] = make_float2(mag * cs, mag * sn);
+    float ph = atan2f(z1.y, z1.x) - atan2f(z0.y, z0.x) - pa;
+    ph = ph - two_pi * rintf(ph / two_pi);
+    acc += (double)ph + (double)pa;
+  }
+}
+
+int phase_vocoder_impl(const float* spec, int64_t s_row, int64_t s_bin, int64_t s_frame, int64_t rows, int64_t bins,
+                       int64_t frames_in, double rate, const float* phase_advance, float* out, int64_t frames_out,
+                       cudaStream_t stream) {
+  if (rows > 65535) return B200A_EUNSUPPORTED;
+  phase_vocoder_kernel<<<dim3((unsigned)((bins + 127) / 128), (unsigned)rows), 128, 0, stream>>>(
+      reinterpret_cast<const float2*>(spec), s_row, s_bin, s_frame, bins, frames_in, rate, phase_advance,
+      reinterpret_cast<float2*>(out), frames_out);
+  return launch_status();
+}
+
 }  // namespace b200a

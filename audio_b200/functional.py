@@ -27,6 +27,8 @@ __all__ = [
     "spectrogram",
     "inverse_spectrogram",
     "griffinlim",
+    "phase_vocoder",
+    "pitch_shift",
     "melscale_fbanks",
     "linear_fbanks",
     "create_dct",
@@ -250,6 +252,79 @@ def griffinlim(
         step(raw=first_raw and n_iter == 0)
         invert()
     return wave.reshape(shape[:-2] + wave.shape[-1:])
+
+
+def phase_vocoder(complex_specgrams: Tensor, rate: float, phase_advance: Tensor) -> Tensor:
+    """Stretch a complex spectrogram in time by ``rate`` without modifying pitch: ``(..., freq, num_frame)`` ->
+    ``(..., freq, ceil(num_frame / rate))`` (reference functional.py:713-803)."""
+    if rate == 1.0:
+        return complex_specgrams
+    if not complex_specgrams.is_complex():
+        raise ValueError("audio_b200: phase_vocoder expects a complex spectrogram")
+    if not complex_specgrams.is_cuda:
+        raise RuntimeError(
+            f"audio_b200: complex_specgrams is on '{complex_specgrams.device}'. This package runs only hand-written "
+            "sm_100a CUDA kernels; there is no CPU or ATen fallback -- move the tensor (and the module) to a CUDA device."
+        )
+    if complex_specgrams.dtype != torch.complex64:
+        raise TypeError(f"audio_b200: complex_specgrams must be complex64 (got {complex_specgrams.dtype})")
+    _no_autograd(complex_specgrams)
+    _require_cuda_f32(phase_advance, "phase_advance")
+    shape = complex_specgrams.size()
+    n_bins, frames = shape[-2], shape[-1]
+    spec3 = complex_specgrams.reshape(-1, n_bins, frames)
+    rows = spec3.shape[0]
+    pa = phase_advance.reshape(-1).contiguous()
+    if pa.numel() != n_bins:
+        raise RuntimeError(f"phase_advance must have one entry per frequency bin ({n_bins}), got {pa.numel()}")
+    frames_out = int(math.ceil(frames / rate))  # len(torch.arange(0, frames, rate))
+    dev = complex_specgrams.device
+    with torch.cuda.device(dev):
+        out = torch.empty((rows, frames_out, n_bins, 2), dtype=torch.float32, device=dev)
+        rc = _lib.lib().b200a_phase_vocoder(
+            torch.view_as_real(spec3).data_ptr(), spec3.stride(0), spec3.stride(1), spec3.stride(2), rows, n_bins, frames,
+            float(rate), pa.data_ptr(), out.data_ptr(), frames_out, _stream_ptr(dev))
+    _lib.check(rc, "phase_vocoder")
+    res = torch.view_as_complex(out).transpose(-1, -2)  # logical (rows, freq, frames_out) over the frame-major buffer
+    return res.reshape(shape[:-2] + res.shape[1:])
+
+
+def pitch_shift(
+    waveform: Tensor,
+    sample_rate: int,
+    n_steps: int,
+    bins_per_octave: int = 12,
+    n_fft: int = 512,
+    win_length: Optional[int] = None,
+    hop_length: Optional[int] = None,
+    window: Optional[Tensor] = None,
+) -> Tensor:
+    """Shift the pitch of a waveform by ``n_steps`` steps (reference functional.py:1579-1719): STFT -> phase vocoder
+    (rate 2^(-n_steps / bins_per_octave)) -> inverse STFT -> resample back to the original duration -> crop / zero-pad
+    to the input length.  Five kernels of this library, no host round trip."""
+    _require_cuda_f32(waveform, "waveform")
+    if hop_length is None:
+        hop_length = n_fft // 4
+    if win_length is None:
+        win_length = n_fft
+    if window is None:
+        window = torch.hann_window(window_length=win_length, device=waveform.device)
+    shape = waveform.size()
+    flat = waveform.reshape(-1, shape[-1])
+    ori_len = shape[-1]
+    rate = 2.0 ** (-float(n_steps) / bins_per_octave)
+    spec_f = spectrogram(flat, 0, window, n_fft, hop_length, win_length, None, False)
+    phase_advance = torch.linspace(0, math.pi * hop_length, spec_f.shape[-2], device=spec_f.device)[..., None]
+    spec_stretch = phase_vocoder(spec_f, rate, phase_advance)
+    len_stretch = int(round(ori_len / rate))
+    stretched = inverse_spectrogram(spec_stretch, len_stretch, 0, window, n_fft, hop_length, win_length, False)
+    shifted = resample(stretched, int(sample_rate / rate), sample_rate)
+    shift_len = shifted.size()[-1]
+    if shift_len > ori_len:
+        shifted = shifted[..., :ori_len]
+    else:
+        shifted = torch.nn.functional.pad(shifted, [0, ori_len - shift_len])
+    return shifted.reshape(shape[:-1] + shifted.shape[-1:])
 
 
 def _db_groups(shape) -> int:

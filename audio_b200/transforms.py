@@ -24,7 +24,7 @@ from . import functional as F
 from ._plans import FrontendPlan, ResamplePlan
 
 __all__ = ["Spectrogram", "InverseSpectrogram", "GriffinLim", "AmplitudeToDB", "MelScale", "MelSpectrogram", "MFCC", "LFCC", "SpectralCentroid", "Resample",
-           "Speed", "SpeedPerturbation"]
+           "Speed", "SpeedPerturbation", "TimeStretch", "PitchShift"]
 
 
 class Spectrogram(torch.nn.Module):
@@ -527,3 +527,93 @@ class SpeedPerturbation(torch.nn.Module):
     def forward(self, waveform: Tensor, lengths: Optional[Tensor] = None):
         idx = int(torch.randint(len(self.speeders), ()))
         return self.speeders[idx](waveform, lengths)
+
+
+class TimeStretch(torch.nn.Module):
+    r"""Stretch a complex spectrogram in time without modifying pitch (reference _transforms.py:1001-1083):
+    ``(..., freq, num_frame) -> (..., freq, ceil(num_frame / rate))``; buffer ``phase_advance``."""
+
+    __constants__ = ["fixed_rate"]
+
+    def __init__(self, hop_length: Optional[int] = None, n_freq: int = 201, fixed_rate: Optional[float] = None) -> None:
+        super().__init__()
+        self.fixed_rate = fixed_rate
+        n_fft = (n_freq - 1) * 2
+        hop_length = hop_length if hop_length is not None else n_fft // 2
+        self.register_buffer("phase_advance", torch.linspace(0, math.pi * hop_length, n_freq)[..., None])
+
+    def forward(self, complex_specgrams: Tensor, overriding_rate: Optional[float] = None) -> Tensor:
+        if not torch.is_complex(complex_specgrams):
+            warnings.warn(
+                "The input to TimeStretch must be complex type. "
+                "Providing non-complex tensor produces invalid results.",
+                stacklevel=4,
+            )
+        if overriding_rate is None:
+            if self.fixed_rate is None:
+                raise ValueError("If no fixed_rate is specified, must pass a valid rate to the forward method.")
+            rate = self.fixed_rate
+        else:
+            rate = overriding_rate
+        return F.phase_vocoder(complex_specgrams, rate, self.phase_advance)
+
+
+class PitchShift(torch.nn.Module):
+    r"""Shift the pitch of a waveform by ``n_steps`` steps (reference _transforms.py:1674-1780): STFT -> phase vocoder ->
+    inverse STFT -> resample -> crop / pad to the input length.  Buffer ``window``; the resampling taps are built on the
+    first call in the input's dtype on its device, like the reference's lazily materialised ``kernel``."""
+
+    __constants__ = ["sample_rate", "n_steps", "bins_per_octave", "n_fft", "win_length", "hop_length"]
+
+    def __init__(
+        self,
+        sample_rate: int,
+        n_steps: int,
+        bins_per_octave: int = 12,
+        n_fft: int = 512,
+        win_length: Optional[int] = None,
+        hop_length: Optional[int] = None,
+        window_fn: Callable[..., Tensor] = torch.hann_window,
+        wkwargs: Optional[dict] = None,
+    ) -> None:
+        super().__init__()
+        self.n_steps = n_steps
+        self.bins_per_octave = bins_per_octave
+        self.sample_rate = sample_rate
+        self.n_fft = n_fft
+        self.win_length = win_length if win_length is not None else n_fft
+        self.hop_length = hop_length if hop_length is not None else self.win_length // 4
+        window = window_fn(self.win_length) if wkwargs is None else window_fn(self.win_length, **wkwargs)
+        self.register_buffer("window", window)
+        rate = 2.0 ** (-float(n_steps) / bins_per_octave)
+        self.orig_freq = int(sample_rate / rate)
+        self.gcd = math.gcd(int(self.orig_freq), int(sample_rate))
+        self.width = -1
+        self.kernel = None
+        self._plan = None
+
+    def forward(self, waveform: Tensor) -> Tensor:
+        shape = waveform.size()
+        flat = waveform.reshape(-1, shape[-1])
+        ori_len = shape[-1]
+        rate = 2.0 ** (-float(self.n_steps) / self.bins_per_octave)
+        spec_f = F.spectrogram(flat, 0, self.window, self.n_fft, self.hop_length, self.win_length, None, False)
+        phase_advance = torch.linspace(0, math.pi * self.hop_length, spec_f.shape[-2], device=spec_f.device)[..., None]
+        spec_stretch = F.phase_vocoder(spec_f, rate, phase_advance)
+        stretched = F.inverse_spectrogram(spec_stretch, int(round(ori_len / rate)), 0, self.window, self.n_fft,
+                                          self.hop_length, self.win_length, False)
+        if self.orig_freq != self.sample_rate:
+            if self.kernel is None or self.kernel.device != waveform.device:
+                self.kernel, self.width = F._get_sinc_resample_kernel(
+                    self.orig_freq, self.sample_rate, self.gcd, dtype=waveform.dtype, device=waveform.device)
+                self._plan = ResamplePlan(self.orig_freq // self.gcd, self.sample_rate // self.gcd, self.width)
+            shifted = F._apply_sinc_resample_kernel(stretched, self.orig_freq, self.sample_rate, self.gcd, self.kernel,
+                                                    self.width, self._plan)
+        else:
+            shifted = stretched
+        shift_len = shifted.size()[-1]
+        if shift_len > ori_len:
+            shifted = shifted[..., :ori_len]
+        else:
+            shifted = torch.nn.functional.pad(shifted, [0, ori_len - shift_len])
+        return shifted.reshape(shape[:-1] + shifted.shape[-1:])

@@ -199,6 +199,18 @@ int b200a_griffinlim_update(const float* mag, int64_t stride_row, int64_t stride
                             int32_t normalize, float* proj, int64_t rows, int64_t bins, int64_t frames,
                             b200a_stream stream);
 
+/*
+ * F.phase_vocoder (functional/functional.py:713-803): time-stretch a complex spectrogram by `rate` without changing
+ * pitch.  Output frame t' interpolates the magnitudes of input frames trunc(ts), trunc(ts + 1), ts = float(rate * t'),
+ * and carries the accumulated phase advance; frames_out = ceil(frames_in / rate) (torch.arange(0, frames_in, rate)).
+ *   spec          : complex64, logical [rows][bins][frames_in], strides in complex elements
+ *   phase_advance : [bins] expected phase advance per hop (linspace(0, pi * hop, bins))
+ *   out           : complex64 frame-major [rows][frames_out][bins]
+ */
+int b200a_phase_vocoder(const float* spec, int64_t stride_row, int64_t stride_bin, int64_t stride_frame, int64_t rows,
+                        int64_t bins, int64_t frames_in, double rate, const float* phase_advance, float* out,
+                        int64_t frames_out, b200a_stream stream);
+
 /* ---- Kaldi-compatible features (compliance/kaldi.py: spectrogram :229-316, fbank :514-645, mfcc :669-813) -------- */
 /*
  * Per-frame conditioning and output placement of the Kaldi front end; the transform itself (window, FFT size,

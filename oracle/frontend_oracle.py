@@ -510,3 +510,50 @@ def griffinlim(specgram, window, n_fft, hop_length, win_length, power, n_iter, m
         tprev = rebuilt
     out = istft(mag * angles, n_fft, hop_length, win_length, window, length=length)
     return out.reshape(lead + out.shape[-1:])
+
+
+def phase_vocoder(spec, rate, phase_advance):
+    """reference functional.py:713-803 in float64, with the reference's float32 time grid
+    (`torch.arange(0, T, rate, dtype=float32)`: value i is float32(rate * i), neighbours by truncation)."""
+    spec = np.asarray(spec, dtype=np.complex128)
+    if rate == 1.0:
+        return spec
+    lead = spec.shape[:-2]
+    sp = spec.reshape((-1,) + spec.shape[-2:])
+    frames = sp.shape[-1]
+    n_out = int(math.ceil(frames / rate))
+    ts = (rate * np.arange(n_out, dtype=np.float64)).astype(np.float32)
+    alphas = np.fmod(ts, np.float32(1.0)).astype(np.float64)
+    i0 = ts.astype(np.int64)
+    i1 = (ts + np.float32(1.0)).astype(np.int64)
+    phase_0 = np.angle(sp[..., :1])
+    padded = np.concatenate([sp, np.zeros(sp.shape[:-1] + (2,), dtype=sp.dtype)], axis=-1)
+    s0, s1 = padded[..., i0], padded[..., i1]
+    pa = np.asarray(phase_advance, dtype=np.float64).reshape(-1, 1)
+    phase = np.angle(s1) - np.angle(s0) - pa
+    phase = phase - 2 * math.pi * np.round(phase / (2 * math.pi))
+    phase = phase + pa
+    phase = np.concatenate([phase_0, phase[..., :-1]], axis=-1)
+    acc = np.cumsum(phase, axis=-1)
+    mag = alphas * np.abs(s1) + (1 - alphas) * np.abs(s0)
+    out = mag * np.exp(1j * acc)
+    return out.reshape(lead + out.shape[1:])
+
+
+def pitch_shift(x, sample_rate, n_steps, bins_per_octave=12, n_fft=512, win_length=None, hop_length=None, window=None):
+    """reference functional.py:1579-1719."""
+    x = np.asarray(x, dtype=np.float64)
+    hop_length = n_fft // 4 if hop_length is None else hop_length
+    win_length = n_fft if win_length is None else win_length
+    window = hann_window(win_length) if window is None else np.asarray(window, dtype=np.float64)
+    lead = x.shape[:-1]
+    flat = x.reshape(-1, x.shape[-1])
+    ori_len = x.shape[-1]
+    rate = 2.0 ** (-float(n_steps) / bins_per_octave)
+    spec = stft(flat, n_fft, hop_length, window, center=True, pad_mode="reflect")
+    pa = np.linspace(0, math.pi * hop_length, spec.shape[-2])[:, None]
+    stretched = istft(phase_vocoder(spec, rate, pa), n_fft, hop_length, win_length, window, length=int(round(ori_len / rate)))
+    shifted = resample(stretched, int(sample_rate / rate), sample_rate)
+    n = shifted.shape[-1]
+    shifted = shifted[..., :ori_len] if n > ori_len else np.concatenate([shifted, np.zeros((shifted.shape[0], ori_len - n))], -1)
+    return shifted.reshape(lead + (ori_len,))

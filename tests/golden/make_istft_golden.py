@@ -78,6 +78,25 @@ def griffinlim_goldens():
     print("griffinlim_goldens.npz", {k: v.shape for k, v in out.items()})
 
 
+def vocoder_goldens():
+    """Reference outputs (CPU float32) of F.phase_vocoder and F.pitch_shift."""
+    import math
+
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 6000, generator=g)
+    w = torch.hann_window(512)
+    spec = F.spectrogram(x, 0, w, 512, 128, 512, None, False)
+    pa = torch.linspace(0, math.pi * 128, 257)[..., None]
+    out = {"wave": x.numpy(), "spec": spec.numpy()}
+    for rate in (0.8, 1.3, 2.0):
+        out[f"pv_{rate}"] = F.phase_vocoder(spec, rate, pa).numpy()
+    for tag, (sr, steps) in {"up12": (16000, 12), "down12": (16000, -12), "up7_1k": (1000, 7), "down5_1k": (1000, -5)}.items():
+        out[f"ps_{tag}"] = F.pitch_shift(x, sr, steps).numpy()
+    np.savez_compressed(os.path.join(HERE, "vocoder_ref_cases.npz"), **out)
+    print("vocoder_ref_cases.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     main()
     griffinlim_goldens()
+    vocoder_goldens()

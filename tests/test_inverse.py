@@ -181,3 +181,80 @@ def test_gpu_griffinlim_module_defaults(gl_goldens):
     assert torch.equal(a, b)
     rel_r = (T.Spectrogram(n_fft=512, hop_length=128, power=2.0).cuda()(a) - spec).norm() / spec.norm()
     assert rel_r.item() < 0.35
+
+
+# ---- phase vocoder / TimeStretch / PitchShift -----------------------------------------------------
+@pytest.fixture(scope="module")
+def vocoder_ref():
+    return np.load(os.path.join(GOLDEN, "vocoder_ref_cases.npz"))
+
+
+PITCH_CASES = {"up12": (16000, 12), "down12": (16000, -12), "up7_1k": (1000, 7), "down5_1k": (1000, -5)}
+
+
+def test_oracle_vocoder_matches_reference(vocoder_ref):
+    """float64 oracle vs the reference's float32 run: the reference accumulates thousands of radians of phase in
+    float32 (~1e-3 rad of round-off), which bounds the agreement at ~1e-3 of the largest magnitude."""
+    import math
+
+    pa = np.linspace(0, math.pi * 128, 257)
+    for rate in (0.8, 1.3, 2.0):
+        got, exp = O.phase_vocoder(vocoder_ref["spec"], rate, pa), vocoder_ref[f"pv_{rate}"]
+        assert got.shape == exp.shape
+        assert np.abs(got - exp).max() <= 2e-3 * np.abs(exp).max()
+        assert np.abs(np.abs(got) - np.abs(exp)).max() <= 1e-5 * np.abs(exp).max()  # magnitudes carry no phase round-off
+    for tag, (sr, steps) in PITCH_CASES.items():
+        got, exp = O.pitch_shift(vocoder_ref["wave"], sr, steps), vocoder_ref[f"ps_{tag}"]
+        assert got.shape == exp.shape and np.abs(got - exp).max() <= 2e-3 * np.abs(exp).max(), tag
+
+
+def test_vocoder_surface_cpu():
+    import audio_b200.transforms as T
+
+    ts = T.TimeStretch(hop_length=128, n_freq=257, fixed_rate=1.3)
+    assert tuple(ts.phase_advance.shape) == (257, 1) and set(ts.state_dict()) == {"phase_advance"}
+    with pytest.raises(ValueError, match="must pass a valid rate"):
+        T.TimeStretch()(torch.zeros(1, 201, 5, dtype=torch.complex64))
+    ps = T.PitchShift(16000, 4)
+    assert (ps.n_fft, ps.win_length, ps.hop_length, ps.orig_freq, ps.gcd) == (512, 512, 128, 20158, 2)
+    x = torch.zeros(1, 257, 5, dtype=torch.complex64)
+    assert T.TimeStretch(fixed_rate=1.0, n_freq=257)(x) is x  # rate 1: returned as is, like the reference
+
+
+@pytest.mark.gpu
+def test_gpu_phase_vocoder_and_time_stretch(vocoder_ref):
+    import math
+
+    import audio_b200.transforms as T
+
+    spec = torch.from_numpy(vocoder_ref["spec"]).cuda()
+    pa = np.linspace(0, math.pi * 128, 257)
+    for rate in (0.8, 1.3, 2.0):
+        got = T.TimeStretch(hop_length=128, n_freq=257, fixed_rate=rate).cuda()(spec)
+        exp, ora = vocoder_ref[f"pv_{rate}"], O.phase_vocoder(vocoder_ref["spec"], rate, pa)
+        assert tuple(got.shape) == exp.shape and got.dtype == torch.complex64
+        g = got.cpu().numpy()
+        scale = np.abs(ora).max()
+        assert np.abs(g - ora).max() <= 1e-4 * scale, rate   # phase carried in double: closer to float64 than the reference
+        assert np.abs(g - exp).max() <= 2e-3 * scale, rate   # the reference's own float32 phase round-off
+    got = T.TimeStretch(n_freq=257)(spec.reshape(1, 2, 257, -1), 1.3)
+    assert tuple(got.shape) == (1, 2, 257, 37)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", list(PITCH_CASES))
+def test_gpu_pitch_shift(vocoder_ref, tag):
+    import audio_b200.functional as F
+    import audio_b200.transforms as T
+
+    sr, steps = PITCH_CASES[tag]
+    x = torch.from_numpy(vocoder_ref["wave"]).cuda()
+    exp = vocoder_ref[f"ps_{tag}"]
+    ora = O.pitch_shift(vocoder_ref["wave"], sr, steps)
+    scale = np.abs(ora).max()
+    got = F.pitch_shift(x, sr, steps).cpu().numpy()
+    assert got.shape == exp.shape
+    assert np.abs(got - ora).max() <= 1e-3 * scale and np.abs(got - exp).max() <= 2e-3 * scale
+    mod = T.PitchShift(sr, steps).cuda()
+    got_m = mod(x.reshape(1, 2, -1)).cpu().numpy()
+    assert got_m.shape == (1, 2, 6000) and np.abs(got_m[0] - got).max() <= 1e-5 * scale
