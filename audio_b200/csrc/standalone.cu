@@ -190,7 +190,6 @@ __global__ void __launch_bounds__(128) phase_vocoder_kernel(const float2* __rest
   const float2* sp = spec + r * s_row + k * s_bin;
   float2* o = out + r * frames_out * bins + k;
   const float pa = phase_advance[k];
-  const float two_pi = 6.283185307179586f;
   const float2 first = sp[0];
   // the accumulated phase grows to thousands of radians: carried in double so that its round-off (1e-3 rad in the
   // reference's float32 cumsum) does not reach the output
@@ -206,9 +205,10 @@ __global__ void __launch_bounds__(128) phase_vocoder_kernel(const float2* __rest
     float sn, cs;
     sincosf((float)(acc - 6.283185307179586 * rint(acc / 6.283185307179586)), &sn, &cs);
     o[t * bins] = make_float2(mag * cs, mag * sn);
-    float ph = atan2f(z1.y, z1.x) - atan2f(z0.y, z0.x) - pa;
-    ph = ph - two_pi * rintf(ph / two_pi);
-    acc += (double)ph + (double)pa;
+    // the expected advance reaches hundreds of radians at the top bins: subtract and wrap in double as well
+    double ph = (double)atan2f(z1.y, z1.x) - (double)atan2f(z0.y, z0.x) - (double)pa;
+    ph -= 6.283185307179586 * rint(ph / 6.283185307179586);
+    acc += ph + (double)pa;
   }
 }
 
