@@ -237,7 +237,7 @@ def test_gpu_phase_vocoder_and_time_stretch(vocoder_ref):
         scale = np.abs(ora).max()
         assert np.abs(g - ora).max() <= 1e-4 * scale, rate   # phase carried in double: closer to float64 than the reference
         assert np.abs(g - exp).max() <= 2e-3 * scale, rate   # the reference's own float32 phase round-off
-    got = T.TimeStretch(n_freq=257)(spec.reshape(1, 2, 257, -1), 1.3)
+    got = T.TimeStretch(n_freq=257).cuda()(spec.reshape(1, 2, 257, -1), 1.3)
     assert tuple(got.shape) == (1, 2, 257, 37)
 
 
