@@ -325,7 +325,7 @@ __device__ __forceinline__ void issue_bulk(const Pow2Params& p, int half, int64_
 //   stage      where a prefetched unit was staged (aliases `tile` when STAGE_IS_TILE)
 //   STAGE_IS_TILE  the staging buffer is the transpose tile itself: the NEXT unit's bulk copy is issued
 //                  only after pass 2 has read the tile back
-template <int POWER_MODE, int G, int HG, bool STAGE_IS_TILE>
+template <int POWER_MODE, int G, int HG, bool STAGE_IS_TILE, bool KALDI>
 __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float (&wreg)[32], const float2* s_tw,
                                                float2* tile, float* stage, uint64_t* bar, uint32_t& parity,
                                                bool& staged, const UnitCursor& cur, int half, int lane,
@@ -349,7 +349,7 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
   if (staged) {
     mbar_wait(bar, parity);
     parity ^= 1;
-  } else if ((!interior || p.kaldi) && p.stage_ok) {
+  } else if ((!interior || KALDI) && p.stage_ok) {
     // edge unit (padding / reflection / ragged end): the lanes gather the unit's whole span into the (idle)
     // staging buffer with 4-byte asynchronous copies -- every sample once, all copies in flight together --
     // and the unit then takes the same register-load path as a bulk-staged one
@@ -383,7 +383,7 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
     __syncwarp();
     from_stage = true;
   }
-  if (from_stage && p.kaldi) {
+  if (KALDI && from_stage) {
     // Kaldi conditioning of the two staged frames (sample n = l + G j, n < win): DC removal, [raw log energy],
     // pre-emphasis s[n] - c s[max(n - 1, 0)], window (zero beyond win), [log energy after the window]
     const float* fa = stage + 2 * gi * p.hop;
@@ -560,7 +560,7 @@ __device__ __forceinline__ void load_window(const Pow2Params& p, int lane, float
 // ------------------------------------------------------------------------------------------------
 // Spectrogram kernel: 8 independent warps, power spectra straight to global memory.
 // ------------------------------------------------------------------------------------------------
-template <int POWER_MODE, int G, int HG, int NW, bool STAGE_IS_TILE>
+template <int POWER_MODE, int G, int HG, int NW, bool STAGE_IS_TILE, bool KALDI>
 __global__ void __launch_bounds__(NW * 32, 1) stft_pow2_power_kernel(const Pow2Params p) {
   using Ge = Geo<G>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -592,19 +592,20 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_pow2_power_kernel(const Pow2P
   }
   for (; cur.u < p.total_units; cur.advance()) {
     float pa[17], pb[17];
-    transform_unit<POWER_MODE, G, HG, STAGE_IS_TILE>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa, pb);
+    transform_unit<POWER_MODE, G, HG, STAGE_IS_TILE, KALDI>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
+                                                            pb);
     const int64_t ta = cur.ub * Ge::kFrames + 2 * gi;
     const bool has_a = ta < p.frames, has_b = ta + 1 < p.frames;
     float* oa = p.out + (cur.row * p.frames + ta) * p.out_width + p.out_col0;
     float* ob = oa + p.out_width;
-    if (p.k_log) {  // Kaldi spectrogram: log(max(|X|^2, eps)), kaldi.py:310
+    if (KALDI && p.k_log) {  // Kaldi spectrogram: log(max(|X|^2, eps)), kaldi.py:310
 #pragma unroll
       for (int m = 0; m < 17; ++m) {
         pa[m] = logf(fmaxf(pa[m], kKaldiEps));
         pb[m] = logf(fmaxf(pb[m], kKaldiEps));
       }
     }
-    const int skip = p.k_energy_col - p.out_col0;  // the bin whose column holds the frame's log energy (-1: none)
+    const int skip = KALDI ? p.k_energy_col - p.out_col0 : -1;  // the bin whose column holds the frame's log energy
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
       if (l + G * m == skip) continue;
@@ -697,7 +698,7 @@ __device__ __forceinline__ void contract_tile(const Pow2Params& p, const MelPlan
 // ------------------------------------------------------------------------------------------------
 constexpr int kFftRegs = 200, kMelRegs = 96;  // 256*200 + 128*96 = 63488 <= 64512 = 384 * 168
 
-template <int POWER_MODE, int G, int HG, int FFT_REGS>
+template <int POWER_MODE, int G, int HG, int FFT_REGS, bool KALDI>
 __device__ __forceinline__ void mel_body_mma(const Pow2Params& p, unsigned char* smem_raw) {
   using Ge = Geo<G>;
   constexpr int kSlots = Ge::kSlots, kPitch = Ge::kPitch;
@@ -765,7 +766,7 @@ __device__ __forceinline__ void mel_body_mma(const Pow2Params& p, unsigned char*
       const bool valid = cur.u < p.total_units;
       float pa[17], pb[17];
       if (valid)
-        transform_unit<POWER_MODE, G, HG, true>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
+        transform_unit<POWER_MODE, G, HG, true, KALDI>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
                                                 pb);
       const int b = it & 1;
       if (it >= 2) mbar_wait(s_empty + b, ((it >> 1) & 1) ^ 1);  // the mel warps have drained this buffer
@@ -1181,7 +1182,7 @@ __device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t& hi, uin
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(ry), "f"(rx));
 }
 
-template <int POWER_MODE, int G, int HG>
+template <int POWER_MODE, int G, int HG, bool KALDI>
 __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* smem_raw) {
   using Ge = Geo<G>;
   using Tc = TcGeo<G>;
@@ -1268,7 +1269,7 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
       const bool valid = cur.u < p.total_units;
       float pa[17], pb[17];
       if (valid)
-        transform_unit<POWER_MODE, G, HG, true>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
+        transform_unit<POWER_MODE, G, HG, true, KALDI>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
                                                 pb);
       const int b = it % NB;
       if (it >= NB) mbar_wait(s_mma + b, ((it / NB) & 1) ^ 1);  // the tensor core has consumed this buffer
@@ -1511,15 +1512,15 @@ __global__ void prepare_tc_kernel(const float* __restrict__ fb, int n_bins, int 
 
 // The mel / MFCC-feature kernel: tcgen05 contraction when the prepared plan says the banded filterbank fits
 // shared memory (every real mel / linear filterbank does), mma.sync contraction otherwise.
-template <int POWER_MODE, int G, int HG>
+template <int POWER_MODE, int G, int HG, bool KALDI>
 __global__ void __launch_bounds__(TcGeo<G>::kThreads, 1) stft_pow2_mel_kernel(const Pow2Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // 512 threads start with 128 registers each: 8 x 32 x 192 + 4 x 32 x 96 + 4 x 32 x 24 <= 65536
   constexpr int kMmaFftRegs = TcGeo<G>::kThreads == 512 ? 192 : kFftRegs;
   if (p.tc != nullptr && p.tc->ok)
-    mel_body_tc<POWER_MODE, G, HG>(p, smem_raw);
+    mel_body_tc<POWER_MODE, G, HG, KALDI>(p, smem_raw);
   else
-    mel_body_mma<POWER_MODE, G, HG, kMmaFftRegs>(p, smem_raw);
+    mel_body_mma<POWER_MODE, G, HG, kMmaFftRegs, KALDI>(p, smem_raw);
 }
 
 // ---- table preparation ------------------------------------------------------------------------
@@ -1661,7 +1662,8 @@ static int launch_power(const Pow2Params& p, cudaStream_t stream) {
   constexpr int NW = 16;
   constexpr bool kShare = true;  // the staged input lives in the warp's transpose tile
   const size_t smem = sizeof(float2) * (32 * 32 + NW * Ge::kTileF2) + sizeof(uint64_t) * NW;
-  auto kern = stft_pow2_power_kernel<POWER_MODE, G, HG, NW, kShare>;
+  auto kern = p.kaldi ? stft_pow2_power_kernel<POWER_MODE, G, -1, NW, kShare, true>
+                      : stft_pow2_power_kernel<POWER_MODE, G, HG, NW, kShare, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return B200A_ECUDA;
   const int64_t grid = persistent_grid(p, NW);
@@ -1681,7 +1683,7 @@ static int launch_mel(const Pow2Params& p, cudaStream_t stream) {
   if (smem > 227 * 1024) return B200A_EUNSUPPORTED;
   static_assert(TcGeo<G>::kFixed + TcGeo<G>::kBBudget <= 227 * 1024 && TcGeo<G>::kBBudget >= 24 * 1024, "tcgen05 layout");
   constexpr int kThreads = TcGeo<G>::kThreads;
-  auto kern = stft_pow2_mel_kernel<POWER_MODE, G, HG>;
+  auto kern = p.kaldi ? stft_pow2_mel_kernel<POWER_MODE, G, -1, true> : stft_pow2_mel_kernel<POWER_MODE, G, HG, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return B200A_ECUDA;
   const int64_t grid = persistent_grid(p, p.tc != nullptr ? TcGeo<G>::NW : kWarps);
