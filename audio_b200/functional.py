@@ -41,6 +41,21 @@ __all__ = [
 ]
 
 
+_PLAN_CACHE: "dict[tuple, FrontendPlan]" = {}
+
+
+def _plan_for(desc, device) -> FrontendPlan:
+    """One FrontendPlan per (descriptor, device) for the functional entry points, so that repeated calls reuse the
+    prepared workspace (the plan itself re-prepares when the window / filterbank tensors change)."""
+    key = (tuple(None if (isinstance(v, float) and v != v) else v for v in desc.key()), str(device))  # NaN power -> None
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        if len(_PLAN_CACHE) >= 64:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+        plan = _PLAN_CACHE[key] = FrontendPlan(desc)
+    return plan
+
+
 def _get_spec_norms(normalized: Union[str, bool]):
     """(frame_length_norm, window_norm) -- reference functional.py:228-242."""
     if isinstance(normalized, str):
@@ -83,7 +98,7 @@ def spectrogram(
         )
     fl_norm, win_norm = _get_spec_norms(normalized)
     desc = FrontendPlan.make_desc(n_fft, win_length, hop_length, pad, center, pad_mode, onesided, fl_norm, win_norm, power)
-    plan = FrontendPlan(desc)
+    plan = _plan_for(desc, waveform.device)
     ws = plan.workspace(window, None, None)
     stage = _lib.STAGE_COMPLEX if power is None else _lib.STAGE_POWER
     return _unpack(plan.run(ws, stage, waveform), waveform)
@@ -151,7 +166,7 @@ def inverse_spectrogram(
     spec3 = spectrogram.reshape(-1, n_bins, frames)
     rows = spec3.shape[0]
     desc = FrontendPlan.make_desc(n_fft, win_length, hop_length, 0, center, "reflect", True, fl_norm, win_norm, 2.0)
-    plan = FrontendPlan(desc)
+    plan = _plan_for(desc, spectrogram.device)
     ws = plan.workspace(window, None, None)
     expected = n_fft + hop_length * (frames - 1)
     start = n_fft // 2 if center else 0
@@ -206,7 +221,7 @@ def griffinlim(
     rows = spec3.shape[0]
     dev = specgram.device
     desc = FrontendPlan.make_desc(n_fft, win_length, hop_length, 0, True, "reflect", True, False, False, None)
-    plan = FrontendPlan(desc)
+    plan = _plan_for(desc, dev)
     ws = plan.workspace(window, None, None)
     expected = n_fft + hop_length * (frames - 1)
     start = n_fft // 2
