@@ -12,7 +12,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libb200audio.so")
+# B200A_LIB: load another build of the same ABI (A/B timing of kernel changes); the default is the in-tree build
+LIB_PATH = os.environ.get("B200A_LIB") or os.path.join(_PKG, "lib", "libb200audio.so")
 
 OK, EINVAL, EUNSUPPORTED, ESHORT, EWORKSPACE, ECUDA = 0, -1, -2, -3, -4, -5
 PAD_MODE = {"reflect": 0, "constant": 1, "replicate": 2, "circular": 3}

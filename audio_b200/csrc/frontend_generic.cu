@@ -129,6 +129,108 @@ __device__ __forceinline__ float kaldi_sample(const float* __restrict__ x, int64
   return x[j];
 }
 
+// ------------------------------------------------------------------------------------------
+// Stockham autosort FFT of `pairs` signals of N points in shared memory (forward transform, twiddles W^q in tw[q]).
+// Radix 2 / 3 / 4 / 5 stages: ONE BUTTERFLY PER THREAD -- R inputs are read once, twiddled (R-1 complex multiplies),
+// passed through the radix's few-multiply DFT and written to their R outputs.  Any other prime radix: one OUTPUT per
+// thread with the direct R-term sum.  Returns the buffer that holds the result (natural order); the other one is free.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+
+template <int R>
+__device__ __forceinline__ void butterfly_stage(const float2* __restrict__ src, float2* __restrict__ dst,
+                                                const float2* __restrict__ tw, int N, int Ns, int pairs, int tid,
+                                                int nthr) {
+  const int NR = N / R, span = Ns * R, step = N / span;
+  for (int b = tid; b < pairs * NR; b += nthr) {
+    const int pr = b / NR, j = b - pr * NR;
+    const int blk = j / Ns, k = j - blk * Ns;
+    const float2* in = src + (size_t)pr * N + j;
+    float2 x[R];
+    x[0] = in[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r) x[r] = cmulf(in[(size_t)r * NR], tw[r * k * step]);
+    float2* out = dst + (size_t)pr * N + blk * span + k;
+    if constexpr (R == 2) {
+      out[0] = cadd(x[0], x[1]);
+      out[Ns] = csub(x[0], x[1]);
+    } else if constexpr (R == 3) {
+      const float2 s = cadd(x[1], x[2]), d = csub(x[1], x[2]);
+      const float2 m = make_float2(fmaf(-0.5f, s.x, x[0].x), fmaf(-0.5f, s.y, x[0].y));
+      const float2 n = make_float2(0.86602540378443865f * d.y, -0.86602540378443865f * d.x);
+      out[0] = cadd(x[0], s);
+      out[Ns] = cadd(m, n);
+      out[2 * Ns] = csub(m, n);
+    } else if constexpr (R == 4) {
+      const float2 t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]), t2 = cadd(x[1], x[3]), t3 = mul_neg_i(csub(x[1], x[3]));
+      out[0] = cadd(t0, t2);
+      out[Ns] = cadd(t1, t3);
+      out[2 * Ns] = csub(t0, t2);
+      out[3 * Ns] = csub(t1, t3);
+    } else {  // R == 5
+      constexpr float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
+      constexpr float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+      const float2 a = cadd(x[1], x[4]), bb = cadd(x[2], x[3]), c = csub(x[1], x[4]), d = csub(x[2], x[3]);
+      const float2 p1 = make_float2(fmaf(c1, a.x, fmaf(c2, bb.x, x[0].x)), fmaf(c1, a.y, fmaf(c2, bb.y, x[0].y)));
+      const float2 p2 = make_float2(fmaf(c2, a.x, fmaf(c1, bb.x, x[0].x)), fmaf(c2, a.y, fmaf(c1, bb.y, x[0].y)));
+      const float2 q1 = mul_neg_i(make_float2(fmaf(s1, c.x, s2 * d.x), fmaf(s1, c.y, s2 * d.y)));
+      const float2 q2 = mul_neg_i(make_float2(fmaf(s2, c.x, -s1 * d.x), fmaf(s2, c.y, -s1 * d.y)));
+      out[0] = cadd(x[0], cadd(a, bb));
+      out[Ns] = cadd(p1, q1);
+      out[2 * Ns] = cadd(p2, q2);
+      out[3 * Ns] = csub(p2, q2);
+      out[4 * Ns] = csub(p1, q1);
+    }
+  }
+}
+
+__device__ __forceinline__ float2* stockham_fft(float2* buf0, float2* buf1, const float2* tw, int N, int pairs,
+                                                const int* radix, int n_stages, int tid, int nthr) {
+  float2* src = buf0;
+  float2* dst = buf1;
+  int Ns = 1;
+  for (int st = 0; st < n_stages; ++st) {
+    const int R = radix[st];
+    if (R == 4) butterfly_stage<4>(src, dst, tw, N, Ns, pairs, tid, nthr);
+    else if (R == 2) butterfly_stage<2>(src, dst, tw, N, Ns, pairs, tid, nthr);
+    else if (R == 5) butterfly_stage<5>(src, dst, tw, N, Ns, pairs, tid, nthr);
+    else if (R == 3) butterfly_stage<3>(src, dst, tw, N, Ns, pairs, tid, nthr);
+    else {
+      const int span = Ns * R, NR = N / R;
+      const int step_stage = N / span, step_dft = NR;
+      for (int o = tid; o < pairs * N; o += nthr) {
+        const int pr = o / N, i = o - pr * N;
+        const int blk = i / span, rem = i - blk * span;
+        const int q = rem / Ns, k = rem - q * Ns;
+        const float2* in = src + (size_t)pr * N + blk * Ns + k;
+        const int e1 = (k * step_stage + q * step_dft) % N;
+        float2 acc = in[0];
+        int e = e1;
+        for (int r = 1; r < R; ++r) {
+          const float2 v = in[(size_t)r * NR];
+          const float2 w = tw[e];
+          acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
+          acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
+          e += e1;
+          if (e >= N) e -= N;
+        }
+        dst[o] = acc;
+      }
+    }
+    __syncthreads();
+    float2* t = src;
+    src = dst;
+    dst = t;
+    Ns *= R;
+  }
+  return src;
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
@@ -228,40 +330,9 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const GenericParams p
   }
   __syncthreads();
 
-  // ---- Stockham autosort FFT, one output per thread per stage -----------------------------
-  float2* src = buf0;
-  float2* dst = buf1;
-  int Ns = 1;
-  for (int st = 0; st < p.n_stages; ++st) {
-    const int R = p.radix[st];
-    const int span = Ns * R;
-    const int NR = N / R;
-    const int step_stage = N / span;  // exponent step of the inter-stage twiddle
-    const int step_dft = NR;          // exponent step of the R-point DFT kernel
-    for (int o = tid; o < pairs * N; o += nthr) {
-      const int pr = o / N, i = o - pr * N;
-      const int blk = i / span, rem = i - blk * span;
-      const int q = rem / Ns, k = rem - q * Ns;
-      const float2* in = src + (size_t)pr * N + blk * Ns + k;
-      const int e1 = (k * step_stage + q * step_dft) % N;
-      float2 acc = in[0];
-      int e = e1;
-      for (int r = 1; r < R; ++r) {
-        const float2 v = in[(size_t)r * NR];
-        const float2 w = tw[e];
-        acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
-        acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
-        e += e1;
-        if (e >= N) e -= N;
-      }
-      dst[o] = acc;
-    }
-    __syncthreads();
-    float2* t = src;
-    src = dst;
-    dst = t;
-    Ns = span;
-  }
+  // ---- Stockham autosort FFT in shared memory ------------------------------------------------
+  float2* src = stockham_fft(buf0, buf1, tw, N, pairs, p.radix, p.n_stages, tid, nthr);
+  float2* dst = src == buf0 ? buf1 : buf0;
   // `src` now holds Z[k] = A[k] + i B[k] in natural order; `dst` is free.
   const float scale = p.hdr->scale;
   const int n_bins = p.n_bins;
@@ -609,38 +680,7 @@ __global__ void __launch_bounds__(256) istft_frames_kernel(const IstftParams p) 
     buf0[o] = make_float2(a.x - b.y, -(a.y + b.x));
   }
   __syncthreads();
-  float2* src = buf0;
-  float2* dst = buf1;
-  int Ns = 1;
-  for (int st = 0; st < p.n_stages; ++st) {
-    const int R = p.radix[st];
-    const int span = Ns * R;
-    const int NR = N / R;
-    const int step_stage = N / span, step_dft = NR;
-    for (int o = tid; o < pairs * N; o += nthr) {
-      const int pr = o / N, i = o - pr * N;
-      const int blk = i / span, rem = i - blk * span;
-      const int q = rem / Ns, k = rem - q * Ns;
-      const float2* in = src + (size_t)pr * N + blk * Ns + k;
-      const int e1 = (k * step_stage + q * step_dft) % N;
-      float2 acc = in[0];
-      int e = e1;
-      for (int r = 1; r < R; ++r) {
-        const float2 v = in[(size_t)r * NR];
-        const float2 w = tw[e];
-        acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
-        acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
-        e += e1;
-        if (e >= N) e -= N;
-      }
-      dst[o] = acc;
-    }
-    __syncthreads();
-    float2* t = src;
-    src = dst;
-    dst = t;
-    Ns = span;
-  }
+  float2* src = stockham_fft(buf0, buf1, tw, N, pairs, p.radix, p.n_stages, tid, nthr);
   const float gain = 1.f / ((float)N * p.hdr->scale);
   for (int o = tid; o < pairs * N; o += nthr) {
     const int pr = o / N, n = o - pr * N;

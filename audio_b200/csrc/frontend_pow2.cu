@@ -226,6 +226,8 @@ __device__ __forceinline__ int frame_lead(const Pow2Params& p, int n_fft) {
   return p.kaldi ? p.k_off : (p.center ? n_fft / 2 : 0);
 }
 
+constexpr int kComplexOut = 3;  // POWER_MODE of the complex (power = None) Spectrogram kernel
+
 template <int POWER_MODE>  // 2: |.|^2, 0: general exponent (1 handled inside)
 __device__ __forceinline__ float pow_of(float re, float im, float power) {
   if constexpr (POWER_MODE == 2) return fmaf(re, re, im * im);
@@ -539,13 +541,27 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
       mi_ = a[slot0].y;
     }
     const float zr = a[slot].x, zi = a[slot].y;
-    pa[m] = pow_of<POWER_MODE>(zr + mr, zi - mi_, p.power);
-    pb[m] = pow_of<POWER_MODE>(zi + mi_, mr - zr, p.power);
+    if constexpr (POWER_MODE == kComplexOut) {  // power = None: the two spectra go straight to out[row][t][bin] (complex64)
+      float2* oc = reinterpret_cast<float2*>(p.out) + (row * p.frames + ta) * Ge::kBins + l + G * m;
+      if (has_a) oc[0] = make_float2(zr + mr, zi - mi_);
+      if (has_b) oc[Ge::kBins] = make_float2(zi + mi_, mr - zr);
+    } else {
+      pa[m] = pow_of<POWER_MODE>(zr + mr, zi - mi_, p.power);
+      pb[m] = pow_of<POWER_MODE>(zi + mi_, mr - zr, p.power);
+    }
   });
   // bin N/2 (l == 0, m = 16) is its own mirror: A = Re, B = Im  (x2 because wreg carries the 1/2)
   constexpr int slot16 = (16 % NG) * G + 16 / NG;
-  pa[16] = pow_of<POWER_MODE>(2.f * a[slot16].x, 0.f, p.power);
-  pb[16] = pow_of<POWER_MODE>(2.f * a[slot16].y, 0.f, p.power);
+  if constexpr (POWER_MODE == kComplexOut) {
+    if (l == 0) {
+      float2* oc = reinterpret_cast<float2*>(p.out) + (row * p.frames + ta) * Ge::kBins + Ge::kNfft / 2;
+      if (has_a) oc[0] = make_float2(2.f * a[slot16].x, 0.f);
+      if (has_b) oc[Ge::kBins] = make_float2(2.f * a[slot16].y, 0.f);
+    }
+  } else {
+    pa[16] = pow_of<POWER_MODE>(2.f * a[slot16].x, 0.f, p.power);
+    pb[16] = pow_of<POWER_MODE>(2.f * a[slot16].y, 0.f, p.power);
+  }
 }
 
 template <int G>
@@ -594,6 +610,7 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_pow2_power_kernel(const Pow2P
     float pa[17], pb[17];
     transform_unit<POWER_MODE, G, HG, STAGE_IS_TILE, KALDI>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
                                                             pb);
+    if constexpr (POWER_MODE == kComplexOut) continue;  // transform_unit has written the complex spectra
     const int64_t ta = cur.ub * Ge::kFrames + 2 * gi;
     const bool has_a = ta < p.frames, has_b = ta + 1 < p.frames;
     float* oa = p.out + (cur.row * p.frames + ta) * p.out_width + p.out_col0;
@@ -1662,8 +1679,9 @@ static int launch_power(const Pow2Params& p, cudaStream_t stream) {
   constexpr int NW = 16;
   constexpr bool kShare = true;  // the staged input lives in the warp's transpose tile
   const size_t smem = sizeof(float2) * (32 * 32 + NW * Ge::kTileF2) + sizeof(uint64_t) * NW;
-  auto kern = p.kaldi ? stft_pow2_power_kernel<POWER_MODE, G, -1, NW, kShare, true>
-                      : stft_pow2_power_kernel<POWER_MODE, G, HG, NW, kShare, false>;
+  auto kern = stft_pow2_power_kernel<POWER_MODE, G, HG, NW, kShare, false>;
+  if constexpr (POWER_MODE != kComplexOut)
+    if (p.kaldi) kern = stft_pow2_power_kernel<POWER_MODE, G, -1, NW, kShare, true>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return B200A_ECUDA;
   const int64_t grid = persistent_grid(p, NW);
@@ -1694,11 +1712,17 @@ static int launch_mel(const Pow2Params& p, cudaStream_t stream) {
 
 template <int POWER_MODE, int G>
 static int launch_g(const Pow2Params& p, bool mel, cudaStream_t stream) {
-  if constexpr (G == 32) {
-    if (p.bulk_ok && p.hop == 256 && !p.kaldi)  // frame b = frame a shifted by 8 lane-rows: shared register loads
-      return mel ? launch_mel<POWER_MODE, 32, 8>(p, stream) : launch_power<POWER_MODE, 32, 8>(p, stream);
+  if constexpr (POWER_MODE == kComplexOut) {  // complex spectra: only the Spectrogram kernel
+    if constexpr (G == 32)
+      if (p.bulk_ok && p.hop == 256) return launch_power<POWER_MODE, 32, 8>(p, stream);
+    return launch_power<POWER_MODE, G, -1>(p, stream);
+  } else {
+    if constexpr (G == 32) {
+      if (p.bulk_ok && p.hop == 256 && !p.kaldi)  // frame b = frame a shifted by 8 lane-rows: shared register loads
+        return mel ? launch_mel<POWER_MODE, 32, 8>(p, stream) : launch_power<POWER_MODE, 32, 8>(p, stream);
+    }
+    return mel ? launch_mel<POWER_MODE, G, -1>(p, stream) : launch_power<POWER_MODE, G, -1>(p, stream);
   }
-  return mel ? launch_mel<POWER_MODE, G, -1>(p, stream) : launch_power<POWER_MODE, G, -1>(p, stream);
 }
 
 template <int POWER_MODE>
@@ -1733,7 +1757,8 @@ static int launch_eo(const Pow2Params& p, const float2* tw_eo, bool mel, cudaStr
 int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, const float* wave, int64_t rows,
                       int64_t length, int64_t row_stride, int64_t frames, float* out, float* group_max,
                       int64_t rows_per_group, cudaStream_t stream, const b200a_kaldi_desc* kd) {
-  if (!pow2_applicable(*d) || stage == B200A_STAGE_COMPLEX) return B200A_EUNSUPPORTED;
+  if (!pow2_applicable(*d)) return B200A_EUNSUPPORTED;
+  if (stage == B200A_STAGE_COMPLEX && (d->n_fft > 1024 || kd != nullptr)) return B200A_EUNSUPPORTED;
   // Kaldi features with a 256 / 512 / 1024-point FFT; every other size takes the generic kernel
   if (kd != nullptr && d->n_fft > 1024) return B200A_EUNSUPPORTED;
   if (stage >= B200A_STAGE_MEL && mel_tiles(d->n_mels) > kMaxItems) return B200A_EUNSUPPORTED;  // > 512 filters
@@ -1811,6 +1836,7 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
     const float2* tw_eo = reinterpret_cast<const float2*>(base + e.tw_eo);
     return d->power == 2.f ? launch_eo<2>(p, tw_eo, mel, stream) : launch_eo<0>(p, tw_eo, mel, stream);
   }
+  if (stage == B200A_STAGE_COMPLEX) return launch_any<kComplexOut>(p, d->n_fft, false, stream);
   return d->power == 2.f ? launch_any<2>(p, d->n_fft, mel, stream) : launch_any<0>(p, d->n_fft, mel, stream);
 }
 

@@ -27,6 +27,16 @@ __all__ = ["Spectrogram", "InverseSpectrogram", "GriffinLim", "AmplitudeToDB", "
            "Speed", "SpeedPerturbation", "TimeStretch", "PitchShift"]
 
 
+def _setup_framing(mod, n_fft, win_length, hop_length, window_fn=None, wkwargs=None, hop_div=2):
+    """The STFT geometry every transform here derives the same way (reference _transforms.py:79-87 and siblings):
+    win_length defaults to n_fft, hop_length to win_length // hop_div, and the window buffer is window_fn(win_length)."""
+    mod.n_fft = n_fft
+    mod.win_length = n_fft if win_length is None else win_length
+    mod.hop_length = mod.win_length // hop_div if hop_length is None else hop_length
+    if window_fn is not None:
+        mod.register_buffer("window", window_fn(mod.win_length, **(wkwargs or {})))
+
+
 class Spectrogram(torch.nn.Module):
     r"""Create a spectrogram from an audio signal: ``(..., time) -> (..., n_fft // 2 + 1, n_frames)``.
 
@@ -51,11 +61,7 @@ class Spectrogram(torch.nn.Module):
         return_complex: Optional[bool] = None,
     ) -> None:
         super().__init__()
-        self.n_fft = n_fft
-        self.win_length = win_length if win_length is not None else n_fft
-        self.hop_length = hop_length if hop_length is not None else self.win_length // 2
-        window = window_fn(self.win_length) if wkwargs is None else window_fn(self.win_length, **wkwargs)
-        self.register_buffer("window", window)
+        _setup_framing(self, n_fft, win_length, hop_length, window_fn, wkwargs)
         self.pad = pad
         self.power = power
         self.normalized = normalized
@@ -109,11 +115,7 @@ class InverseSpectrogram(torch.nn.Module):
         onesided: bool = True,
     ) -> None:
         super().__init__()
-        self.n_fft = n_fft
-        self.win_length = win_length if win_length is not None else n_fft
-        self.hop_length = hop_length if hop_length is not None else self.win_length // 2
-        window = window_fn(self.win_length) if wkwargs is None else window_fn(self.win_length, **wkwargs)
-        self.register_buffer("window", window)
+        _setup_framing(self, n_fft, win_length, hop_length, window_fn, wkwargs)
         self.pad = pad
         self.normalized = normalized
         self.center = center
@@ -253,9 +255,7 @@ class MelSpectrogram(torch.nn.Module):
                 "Argument 'onesided' has been deprecated and has no influence on the behavior of this module."
             )
         self.sample_rate = sample_rate
-        self.n_fft = n_fft
-        self.win_length = win_length if win_length is not None else n_fft
-        self.hop_length = hop_length if hop_length is not None else self.win_length // 2
+        _setup_framing(self, n_fft, win_length, hop_length)
         self.pad = pad
         self.power = power
         self.normalized = normalized
@@ -428,11 +428,7 @@ class SpectralCentroid(torch.nn.Module):
     ) -> None:
         super().__init__()
         self.sample_rate = sample_rate
-        self.n_fft = n_fft
-        self.win_length = win_length if win_length is not None else n_fft
-        self.hop_length = hop_length if hop_length is not None else self.win_length // 2
-        window = window_fn(self.win_length) if wkwargs is None else window_fn(self.win_length, **wkwargs)
-        self.register_buffer("window", window)
+        _setup_framing(self, n_fft, win_length, hop_length, window_fn, wkwargs)
         self.pad = pad
 
     def forward(self, waveform: Tensor) -> Tensor:
@@ -580,11 +576,7 @@ class PitchShift(torch.nn.Module):
         self.n_steps = n_steps
         self.bins_per_octave = bins_per_octave
         self.sample_rate = sample_rate
-        self.n_fft = n_fft
-        self.win_length = win_length if win_length is not None else n_fft
-        self.hop_length = hop_length if hop_length is not None else self.win_length // 4
-        window = window_fn(self.win_length) if wkwargs is None else window_fn(self.win_length, **wkwargs)
-        self.register_buffer("window", window)
+        _setup_framing(self, n_fft, win_length, hop_length, window_fn, wkwargs, hop_div=4)
         rate = 2.0 ** (-float(n_steps) / bins_per_octave)
         self.orig_freq = int(sample_rate / rate)
         self.gcd = math.gcd(int(self.orig_freq), int(sample_rate))
