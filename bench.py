@@ -35,8 +35,8 @@ WORKLOAD = "MelSpectrogram n_fft=1024 hop=256 n_mels=80, batch=256x16kHzx10s fp3
 # compulsory traffic of the fused op = waveform in + mel out + constant tables
 ALGO_BYTES = 4 * (BATCH * LENGTH + BATCH * FRAMES * N_MELS) + 4 * (N_FFT + (N_FFT // 2 + 1) * N_MELS)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused kernel (ncu --set full capture,
-# profiles/r1_stft1024_v5.txt): 164.02 MB + 32.17 MB -- the write-back of the rest is still in L2 at kernel end
-NCU_DRAM_BYTES = 196_193_024
+# profiles/r1_stft1024_v6.txt): 164.02 MB + 35.21 MB -- the write-back of the rest is still in L2 at kernel end
+NCU_DRAM_BYTES = 199_229_440
 
 
 def measured_peaks():
@@ -258,7 +258,7 @@ def run_b200(args):
                        "parallelism": f"batch shard x{world}, no collective",
                        "l2": "input 163.8 MB per step > 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES, "traffic_source": "ncu --set full, profiles/r1_stft1024_v5.txt (dram read+write per launch)", "peak_source": peak_src, "algorithmic_bytes": ALGO_BYTES,
+                         "traffic": NCU_DRAM_BYTES, "traffic_source": "ncu --set full, profiles/r1_stft1024_v6.txt (dram read+write per launch)", "peak_source": peak_src, "algorithmic_bytes": ALGO_BYTES,
                          "kernel": "fused STFT+mel kernel (one launch per step)"},
             "e2e": {"value": frames_job / (ms_e2e / K * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": BATCH * LENGTH * 4, "d2h_bytes_per_step": BATCH * FRAMES * N_MELS * 4,
