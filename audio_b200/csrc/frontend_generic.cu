@@ -715,6 +715,9 @@ __global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict_
   out[row * out_row_stride + sp] = t_hi >= t_lo ? acc / env : 0.f;
 }
 
+int istft_frames_pow2(const b200a_frontend_desc*, const void*, const float*, int64_t, int64_t, int64_t, int64_t, int64_t, float*,
+                      cudaStream_t);  // frontend_pow2.cu; B200A_EUNSUPPORTED when the size is not 256 / 512 / 1024
+
 int istft_run_impl(const b200a_frontend_desc* d, const void* ws, const float* spec, int64_t rows, int64_t frames,
                    int64_t stride_row, int64_t stride_bin, int64_t stride_frame, float* frame_buf, float* out,
                    int64_t out_row_stride, int64_t start, int64_t out_len, cudaStream_t stream) {
@@ -744,8 +747,11 @@ int istft_run_impl(const b200a_frontend_desc* d, const void* ws, const float* sp
     return B200A_ECUDA;
   const int64_t grid = rows * p.tiles_per_row;
   if (grid <= 0 || grid > 0x7fffffffLL || rows > 65535) return B200A_EUNSUPPORTED;
-  istft_frames_kernel<<<(unsigned)grid, 256, smem, stream>>>(p);
-  int rc = launch_status();
+  int rc = istft_frames_pow2(d, ws, spec, rows, frames, stride_row, stride_bin, stride_frame, frame_buf, stream);
+  if (rc == B200A_EUNSUPPORTED) {  // any other size: shared-memory Stockham
+    istft_frames_kernel<<<(unsigned)grid, 256, smem, stream>>>(p);
+    rc = launch_status();
+  }
   if (rc != B200A_OK) return rc;
   const int64_t blocks = (out_len + 255) / 256;
   if (blocks > 0x7fffffffLL) return B200A_EUNSUPPORTED;

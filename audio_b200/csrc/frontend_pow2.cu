@@ -1540,6 +1540,93 @@ __global__ void __launch_bounds__(TcGeo<G>::kThreads, 1) stft_pow2_mel_kernel(co
     mel_body_mma<POWER_MODE, G, HG, kMmaFftRegs, KALDI>(p, smem_raw);
 }
 
+// ================================================================================================
+// Inverse STFT frames on the register FFT (n_fft = 256 / 512 / 1024): the first half of b200a_istft_run.
+// A lane group rebuilds the PAIR of frames (a, b) from their two Hermitian spectra with ONE complex transform:
+//   Z[k] = A[k] + i B[k] (k <= N/2),  Z[N-k] = conj(A[k]) + i conj(B[k]);  z = IFFT(Z) = a + i b
+// computed as conj(FFT(conj Z)) / N with the forward passes of transform_unit (32-point register DFT, twiddle,
+// transpose through the padded tile, G-point register DFTs).  Lane l loads bins n = l + G j and ends with time
+// samples n = l + G m, which it multiplies by window / (N * forward normalisation) and stores to the frame buffer.
+// C2R semantics: the imaginary parts of bins 0 and N/2 are ignored.
+// ================================================================================================
+struct IstftPow2Params {
+  const float2* spec;  // logical [rows][bins][frames], element strides below
+  int64_t stride_row, stride_bin, stride_frame;
+  int64_t frames, units_per_row, total_units;
+  float* frame_buf;  // [rows][frames][n_fft]
+  const float* window;
+  const float2* tw2d;
+  const WsHeader* hdr;
+};
+
+constexpr int kIsWarps = 16;
+
+template <int G>
+__global__ void __launch_bounds__(kIsWarps * 32, 1) istft_pow2_kernel(const IstftPow2Params p) {
+  using Ge = Geo<G>;
+  constexpr int N = Ge::kNfft, NG = Ge::kGroups;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);  // [32][G]
+  float2* s_tile_all = s_tw + 32 * G;                  // [kIsWarps][kTileF2]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 32 * G; i += blockDim.x) s_tw[i] = p.tw2d[i];
+  __syncthreads();
+  float2* grp_tile = s_tile_all + warp * Ge::kTileF2 + (lane / G) * Ge::kRegion;
+  const int gi = lane / G, l = lane % G;
+  float wreg[32];
+  {
+    const float gain = 1.f / ((float)N * p.hdr->scale);
+#pragma unroll
+    for (int m = 0; m < 32; ++m) wreg[m] = p.window[l + G * m] * gain;
+  }
+  UnitCursor cur;
+  cur.init((int64_t)blockIdx.x * kIsWarps + warp, (int64_t)gridDim.x * kIsWarps, p.units_per_row);
+  for (; cur.u < p.total_units; cur.advance()) {
+    const int64_t ta = cur.ub * Ge::kFrames + 2 * gi, tb = ta + 1;
+    const bool has_a = ta < p.frames, has_b = tb < p.frames;
+    const float2* __restrict__ sp = p.spec + cur.row * p.stride_row;
+    float2 a[32];
+    static_for<32>([&](auto ji) {
+      constexpr int j = decltype(ji)::value;
+      const int n = l + G * j;
+      const int kk = n <= N / 2 ? n : N - n;
+      float2 za = make_float2(0.f, 0.f), zb = za;
+      if (has_a) za = __ldg(sp + kk * p.stride_bin + ta * p.stride_frame);
+      if (has_b) zb = __ldg(sp + kk * p.stride_bin + tb * p.stride_frame);
+      if (kk == 0 || kk == N / 2) za.y = zb.y = 0.f;
+      if (n > N / 2) {
+        za.y = -za.y;
+        zb.y = -zb.y;
+      }
+      a[brev5(j)] = make_float2(za.x - zb.y, -(za.y + zb.x));  // conj(Z[n])
+    });
+    fft_regs<32, 0>(a);
+    grp_tile[l] = a[0];
+    static_for<31>([&](auto ki) {
+      constexpr int k2 = decltype(ki)::value + 1;
+      const float2 w = s_tw[k2 * G + l];
+      const float2 v = a[k2];
+      grp_tile[k2 * Ge::kRowLd + l] = make_float2(fmaf(v.x, w.x, -v.y * w.y), fmaf(v.x, w.y, v.y * w.x));
+    });
+    __syncwarp();
+    static_for<32>([&](auto si) {
+      constexpr int s = decltype(si)::value;
+      constexpr int q = s / G, g = s % G;
+      a[q * G + brev<Ge::kLogG>(g)] = grp_tile[(l + G * q) * Ge::kRowLd + g];
+    });
+    __syncwarp();
+    static_for<NG>([&](auto qi) { fft_regs<G, decltype(qi)::value * G>(a); });
+    // a[(m % NG) G + m / NG] = FFT(conj Z)[l + G m] = N (a[n] - i b[n])
+    float* fa = p.frame_buf + (cur.row * p.frames + ta) * N + l;
+    static_for<32>([&](auto mi) {
+      constexpr int m = decltype(mi)::value;
+      constexpr int slot = (m % NG) * G + m / NG;
+      if (has_a) fa[G * m] = a[slot].x * wreg[m];
+      if (has_b) fa[N + G * m] = -a[slot].y * wreg[m];
+    });
+  }
+}
+
 // ---- table preparation ------------------------------------------------------------------------
 __global__ void prepare_tw2d_kernel(float2* tw2d, int G) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = k2 * G + g
@@ -1838,6 +1925,41 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
   }
   if (stage == B200A_STAGE_COMPLEX) return launch_any<kComplexOut>(p, d->n_fft, false, stream);
   return d->power == 2.f ? launch_any<2>(p, d->n_fft, mel, stream) : launch_any<0>(p, d->n_fft, mel, stream);
+}
+
+// First half of b200a_istft_run for n_fft = 256 / 512 / 1024: windowed time frames into frame_buf.
+int istft_frames_pow2(const b200a_frontend_desc* d, const void* ws, const float* spec, int64_t rows, int64_t frames,
+                      int64_t stride_row, int64_t stride_bin, int64_t stride_frame, float* frame_buf, cudaStream_t stream) {
+  if (!pow2_applicable(*d) || d->n_fft > 1024) return B200A_EUNSUPPORTED;
+  const WsLayout l = ws_layout(*d);
+  const Pow2Extra e = pow2_layout(*d, l.total);
+  const unsigned char* base = static_cast<const unsigned char*>(ws);
+  const int G = d->n_fft / 32;
+  const int frames_per_unit = 2 * (32 / G);
+  IstftPow2Params p{};
+  p.spec = reinterpret_cast<const float2*>(spec);
+  p.stride_row = stride_row;
+  p.stride_bin = stride_bin;
+  p.stride_frame = stride_frame;
+  p.frames = frames;
+  p.units_per_row = (frames + frames_per_unit - 1) / frames_per_unit;
+  p.total_units = rows * p.units_per_row;
+  p.frame_buf = frame_buf;
+  p.window = reinterpret_cast<const float*>(base + l.window);
+  p.tw2d = reinterpret_cast<const float2*>(base + e.tw2d);
+  p.hdr = reinterpret_cast<const WsHeader*>(base + l.header);
+  const int sms = num_sms();
+  if (sms < 0) return B200A_ECUDA;
+  const int64_t iters = (p.total_units + kIsWarps - 1) / kIsWarps;
+  const unsigned grid = (unsigned)(iters < sms ? (iters < 1 ? 1 : iters) : sms);
+  auto launch = [&](auto kern, size_t smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return (int)B200A_ECUDA;
+    kern<<<grid, kIsWarps * 32, smem, stream>>>(p);
+    return launch_status();
+  };
+  if (G == 32) return launch(istft_pow2_kernel<32>, sizeof(float2) * (32 * 32 + kIsWarps * Geo<32>::kTileF2));
+  if (G == 16) return launch(istft_pow2_kernel<16>, sizeof(float2) * (32 * 16 + kIsWarps * Geo<16>::kTileF2));
+  return launch(istft_pow2_kernel<8>, sizeof(float2) * (32 * 8 + kIsWarps * Geo<8>::kTileF2));
 }
 
 }  // namespace b200a

@@ -194,12 +194,20 @@ __global__ void __launch_bounds__(128) phase_vocoder_kernel(const float2* __rest
   // the accumulated phase grows to thousands of radians: carried in double so that its round-off (1e-3 rad in the
   // reference's float32 cumsum) does not reach the output
   double acc = (double)atan2f(first.y, first.x);  // phase_0
-  for (int64_t t = 0; t < frames_out; ++t) {
+  // the neighbours of step t + 1 are fetched before step t's arithmetic, so the global-load latency of the walk hides
+  // behind the transcendental chain instead of adding to it
+  auto fetch = [&](int64_t t, float& alpha, float2& z0, float2& z1) {
     const float ts = (float)(rate * (double)t);
-    const float alpha = fmodf(ts, 1.0f);
+    alpha = fmodf(ts, 1.0f);
     const int64_t i0 = (int64_t)ts, i1 = (int64_t)(ts + 1.0f);
-    const float2 z0 = i0 < frames_in ? sp[i0 * s_frame] : make_float2(0.f, 0.f);
-    const float2 z1 = i1 < frames_in ? sp[i1 * s_frame] : make_float2(0.f, 0.f);
+    z0 = (t < frames_out && i0 < frames_in) ? sp[i0 * s_frame] : make_float2(0.f, 0.f);
+    z1 = (t < frames_out && i1 < frames_in) ? sp[i1 * s_frame] : make_float2(0.f, 0.f);
+  };
+  float alpha, alpha_n;
+  float2 z0, z1, z0n, z1n;
+  fetch(0, alpha, z0, z1);
+  for (int64_t t = 0; t < frames_out; ++t) {
+    fetch(t + 1, alpha_n, z0n, z1n);
     const float n0 = hypotf(z0.x, z0.y), n1 = hypotf(z1.x, z1.y);
     const float mag = alpha * n1 + (1.f - alpha) * n0;
     float sn, cs;
@@ -209,6 +217,9 @@ __global__ void __launch_bounds__(128) phase_vocoder_kernel(const float2* __rest
     double ph = (double)atan2f(z1.y, z1.x) - (double)atan2f(z0.y, z0.x) - (double)pa;
     ph -= 6.283185307179586 * rint(ph / 6.283185307179586);
     acc += ph + (double)pa;
+    alpha = alpha_n;
+    z0 = z0n;
+    z1 = z1n;
   }
 }
 
