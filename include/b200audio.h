@@ -136,6 +136,8 @@ int b200a_frontend_run(const b200a_frontend_desc* desc, const void* workspace, i
  *   feat      : [rows][T][n_mels] from B200A_STAGE_FEAT
  *   group_max : [groups] maxima (after any cross-rank all-reduce), NULL or top_db < 0 => no clamp
  *   out       : [rows][T][n_mfcc]
+ * With a clamp the product runs on the tensor pipe in error-compensated TF32 (~2^-21 relative to sum |feat * dct|, inside
+ * the 1e-4 bar of the dB path); without one (log-mel MFCC, Kaldi MFCC) in FP32 FMAs.
  */
 int b200a_mfcc_finish(const b200a_frontend_desc* desc, const void* workspace, const float* feat,
                       int64_t rows, int64_t frames, const float* group_max, int64_t rows_per_group,
