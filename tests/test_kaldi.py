@@ -175,3 +175,23 @@ def test_gpu_batch_extension_and_edges(kaldi_ref):
         K.fbank(x[:1, :300])
     with pytest.raises(AssertionError, match="Invalid channel"):
         K.fbank(x, channel=2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sr", [22050.0, 44100.0, 11025.0])
+@pytest.mark.parametrize("snip", [True, False])
+def test_gpu_other_sample_rates_against_oracle(kaldi_ref, sr, snip):
+    """Frame sizes that are not multiples of 4 samples (551 / 1102 / 275 at 25 ms) and shifts such as 220: the
+    register path stages every unit through the gather (no 16-byte aligned bulk copy), 2048-point frames take the
+    generic kernel."""
+    import audio_b200.compliance.kaldi as K
+
+    x = kaldi_ref["wave"][:1, :15000]
+    kw = dict(sample_frequency=sr, num_mel_bins=40, snip_edges=snip, use_energy=True, low_freq=40.0)
+    got = K.fbank(torch.from_numpy(x).cuda(), **kw).cpu().numpy()
+    exp = KO.fbank(x, **kw)
+    assert got.shape == exp.shape
+    assert np.abs(got - exp).max() <= 2e-5 * np.abs(exp).max() + 1e-4
+    got = K.mfcc(torch.from_numpy(x).cuda(), sample_frequency=sr, snip_edges=snip, num_mel_bins=30, num_ceps=12).cpu().numpy()
+    exp = KO.mfcc(x, sample_frequency=sr, snip_edges=snip, num_mel_bins=30, num_ceps=12)
+    assert got.shape == exp.shape and np.abs(got - exp).max() <= 2e-5 * np.abs(exp).max() + 2e-4
