@@ -59,7 +59,6 @@ constexpr int kMaxSlots = 64;
 // Geometry of one transform size: G lanes per frame pair.
 template <int G>
 struct Geo {
-  static constexpr int kG = G;
   static constexpr int kNfft = 32 * G;
   static constexpr int kBins = kNfft / 2 + 1;
   static constexpr int kGroups = 32 / G;        // frame pairs per warp
