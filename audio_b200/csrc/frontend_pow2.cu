@@ -41,6 +41,7 @@
 #include <utility>
 
 #include "common.cuh"
+#include "f32x2.cuh"
 #include "ptx.cuh"
 
 namespace b200a {
@@ -150,34 +151,33 @@ __device__ constexpr float kSin32[17] = {0.f, 0.19509032201612825f, 0.3826834323
                                          0.83146961230254546f, 0.70710678118654757f, 0.55557023301960218f,
                                          0.38268343236508989f, 0.19509032201612861f, 0.f};
 
-// DIT butterfly (a, b) -> (a + W b, a - W b), W = exp(-2 pi i E / 32), E in [0, 16).
-// General case in FMA form: 3 instructions per real output pair instead of 4.
+// DIT butterfly (a, b) -> (a + W b, a - W b), W = exp(-2 pi i E / 32), E in [0, 16), on packed FP32 pairs
+// (f32x2.cuh): 2 issue slots for the trivial twiddles, 3 for the others (was 4 / 6 with scalar FADD / FFMA).
 template <int E>
 __device__ __forceinline__ void bfly(float2& a, float2& b) {
   if constexpr (E == 0) {
     const float2 t = b;
-    b = make_float2(a.x - t.x, a.y - t.y);
-    a = make_float2(a.x + t.x, a.y + t.y);
-  } else if constexpr (E == 8) {  // W = -i : W b = (b.y, -b.x)
+    b = sub2(a, t);
+    a = add2(a, t);
+  } else if constexpr (E == 8) {  // W = -i : W b = (b.y, -b.x) = -i b
     const float2 t = b;
-    b = make_float2(a.x - t.y, a.y + t.x);
-    a = make_float2(a.x + t.y, a.y - t.x);
-  } else if constexpr (E == 4) {  // W = (1 - i)/sqrt2 : W b = c ((bx + by), (by - bx))
+    b = add_i(a, t);
+    a = sub_i(a, t);
+  } else if constexpr (E == 4) {  // W = (1 - i)/sqrt2 : W b = c (b - i b)
     constexpr float c = 0.70710678118654752f;
-    const float tr = b.x + b.y, ti = b.y - b.x;
-    b = make_float2(fmaf(-c, tr, a.x), fmaf(-c, ti, a.y));
-    a = make_float2(fmaf(c, tr, a.x), fmaf(c, ti, a.y));
-  } else if constexpr (E == 12) {  // W = (-1 - i)/sqrt2 : W b = c ((by - bx), -(bx + by))
+    const float2 t = sub_i(b, b);  // (b.x + b.y, b.y - b.x)
+    b = fmas2(-c, t, a);
+    a = fmas2(c, t, a);
+  } else if constexpr (E == 12) {  // W = (-1 - i)/sqrt2 : W b = -c (b + i b)
     constexpr float c = 0.70710678118654752f;
-    const float tr = b.y - b.x, ti = -(b.x + b.y);
-    b = make_float2(fmaf(-c, tr, a.x), fmaf(-c, ti, a.y));
-    a = make_float2(fmaf(c, tr, a.x), fmaf(c, ti, a.y));
+    const float2 u = add_i(b, b);  // (b.x - b.y, b.y + b.x)
+    b = fmas2(c, u, a);
+    a = fmas2(-c, u, a);
   } else {
     constexpr float wr = kCos32[E], wi = -kSin32[E];
-    const float pr = fmaf(wr, b.x, fmaf(-wi, b.y, a.x));
-    const float pi = fmaf(wr, b.y, fmaf(wi, b.x, a.y));
-    b = make_float2(fmaf(2.f, a.x, -pr), fmaf(2.f, a.y, -pi));
-    a = make_float2(pr, pi);
+    const float2 p = cfma2(wr, wi, b, a);               // a + W b
+    b = fma2(make_float2(2.f, 2.f), a, make_float2(-p.x, -p.y));  // 2 a - p = a - W b
+    a = p;
   }
 }
 
@@ -461,7 +461,7 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
       const float* pb_ptr = pa_ptr + p.hop;
       static_for<32>([&](auto ji) {
         constexpr int j = decltype(ji)::value;
-        a[brev5(j)] = make_float2(pa_ptr[G * j] * wreg[j], pb_ptr[G * j] * wreg[j]);
+        a[brev5(j)] = scale2(wreg[j], make_float2(pa_ptr[G * j], pb_ptr[G * j]));
       });
     }
     __syncwarp();  // every lane has consumed the staging buffer
@@ -470,7 +470,7 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
       constexpr int j = decltype(ji)::value;
       const float va = has_a ? __ldg(x + sa + l + G * j) : 0.f;
       const float vb = has_b ? __ldg(x + sb + l + G * j) : 0.f;
-      a[brev5(j)] = make_float2(va * wreg[j], vb * wreg[j]);
+      a[brev5(j)] = scale2(wreg[j], make_float2(va, vb));
     });
   } else {
     // edge unit whose span does not fit the staging buffer: gather through the group's tile region with a
@@ -486,7 +486,7 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
     static_for<32>([&](auto ji) {
       constexpr int j = decltype(ji)::value;
       const float2 v = grp_tile[l + G * j];
-      a[brev5(j)] = make_float2(v.x * wreg[j], v.y * wreg[j]);
+      a[brev5(j)] = scale2(wreg[j], v);
     });
     __syncwarp();
   }
@@ -503,7 +503,7 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
     constexpr int k2 = decltype(ki)::value + 1;
     const float2 w = s_tw[k2 * G + l];
     const float2 v = a[k2];
-    grp_tile[k2 * Ge::kRowLd + l] = make_float2(fmaf(v.x, w.x, -v.y * w.y), fmaf(v.x, w.y, v.y * w.x));
+    grp_tile[k2 * Ge::kRowLd + l] = cmul2(v, w);
   });
   __syncwarp();
   // lane l now owns k2 = l + G q, q < 32/G: slot q*G + brev(g) <- element (g, l + G q)
@@ -539,14 +539,21 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
       mr = a[slot0].x;
       mi_ = a[slot0].y;
     }
+    // A = Z[k] + conj Z[N-k] = (sx.x, sy.x),  B = (Z[k] - conj Z[N-k]) / i = (sy.y, -sx.y): two packed adds
     const float zr = a[slot].x, zi = a[slot].y;
+    const float2 sx = add2(make_float2(zr, zr), make_float2(mr, -mr));    // (zr + mr, zr - mr)
+    const float2 sy = add2(make_float2(zi, zi), make_float2(-mi_, mi_));  // (zi - mi, zi + mi)
     if constexpr (POWER_MODE == kComplexOut) {  // power = None: the two spectra go straight to out[row][t][bin] (complex64)
       float2* oc = reinterpret_cast<float2*>(p.out) + (row * p.frames + ta) * Ge::kBins + l + G * m;
-      if (has_a) oc[0] = make_float2(zr + mr, zi - mi_);
-      if (has_b) oc[Ge::kBins] = make_float2(zi + mi_, mr - zr);
+      if (has_a) oc[0] = make_float2(sx.x, sy.x);
+      if (has_b) oc[Ge::kBins] = make_float2(sy.y, -sx.y);
+    } else if constexpr (POWER_MODE == 2) {  // (|A|^2, |B|^2) as one packed multiply + one packed FMA
+      const float2 pw = fma2(sx, sx, mul2(sy, sy));
+      pa[m] = pw.x;
+      pb[m] = pw.y;
     } else {
-      pa[m] = pow_of<POWER_MODE>(zr + mr, zi - mi_, p.power);
-      pb[m] = pow_of<POWER_MODE>(zi + mi_, mr - zr, p.power);
+      pa[m] = pow_of<POWER_MODE>(sx.x, sy.x, p.power);
+      pb[m] = pow_of<POWER_MODE>(sy.y, sx.y, p.power);
     }
   });
   // bin N/2 (l == 0, m = 16) is its own mirror: A = Re, B = Im  (x2 because wreg carries the 1/2)
@@ -902,7 +909,7 @@ __device__ __forceinline__ void transform_frame_eo(const Pow2Params& p, const fl
     constexpr int k2 = decltype(ki)::value + 1;
     const float2 w = s_tw[k2 * 32 + lane];
     const float2 v = a[k2];
-    tile[k2 * 33 + lane] = make_float2(fmaf(v.x, w.x, -v.y * w.y), fmaf(v.x, w.y, v.y * w.x));
+    tile[k2 * 33 + lane] = cmul2(v, w);
   });
   __syncwarp();
   static_for<32>([&](auto gi) {
@@ -1605,7 +1612,7 @@ __global__ void __launch_bounds__(kIsWarps * 32, 1) istft_pow2_kernel(const Istf
       constexpr int k2 = decltype(ki)::value + 1;
       const float2 w = s_tw[k2 * G + l];
       const float2 v = a[k2];
-      grp_tile[k2 * Ge::kRowLd + l] = make_float2(fmaf(v.x, w.x, -v.y * w.y), fmaf(v.x, w.y, v.y * w.x));
+      grp_tile[k2 * Ge::kRowLd + l] = cmul2(v, w);
     });
     __syncwarp();
     static_for<32>([&](auto si) {

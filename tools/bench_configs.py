@@ -67,6 +67,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the torchaudio CPU reference timings")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     peak = hbm_peak()
@@ -79,7 +80,7 @@ def main():
             mod = make(T).to(dev)
         with torch.inference_mode():
             ms = time_gpu(lambda: mod(x), iters=5 if args.quick else 20, blocks=3 if args.quick else 5)
-        cpu_s = time_cpu(make, x[:cpu_rows].cpu())
+        cpu_s = None if args.no_cpu else time_cpu(make, x[:cpu_rows].cpu())
         cpu_rate = None if cpu_s is None else units * cpu_rows / x.shape[0] / cpu_s
         rec = {"config": name, "ms": ms, "rate": units / (ms * 1e-3), "unit": unit_name,
                "algorithmic_MB": algo_bytes / 1e6, "achieved_GBs": algo_bytes / (ms * 1e-3) / 1e9,
