@@ -55,6 +55,9 @@ class FrontendPlan:
         self.desc = desc
         self._ws: Optional[torch.Tensor] = None
         self._stamp = None
+        # the constant tensors the workspace was built from: holding them keeps their storage from being
+        # recycled, so an equal (data_ptr, _version) stamp can only mean "the same, unmodified tensor"
+        self._held = None
 
     @staticmethod
     def make_desc(
@@ -123,7 +126,7 @@ class FrontendPlan:
                 _stream_ptr(dev),
             )
         _lib.check(rc, "frontend_prepare")
-        self._ws, self._stamp = ws, stamp
+        self._ws, self._stamp, self._held = ws, stamp, (window, fb, dct)
         return ws
 
     def frames(self, length: int) -> int:
@@ -218,6 +221,7 @@ class ResamplePlan:
         self._ws: Optional[torch.Tensor] = None
         self._stamp = None
         self._kernel: Optional[torch.Tensor] = None
+        self._held = None  # the kernel tensor behind the stamp (see FrontendPlan._held)
 
     def workspace(self, kernel: torch.Tensor):
         stamp = (kernel.data_ptr(), kernel._version, str(kernel.device))
@@ -236,7 +240,7 @@ class ResamplePlan:
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             rc = lib.b200a_resample_prepare(k.data_ptr(), self.orig_r, self.new_r, self.width, ws.data_ptr(), nbytes, _stream_ptr(dev))
         _lib.check(rc, "resample_prepare")
-        self._ws, self._stamp, self._kernel = ws, stamp, k
+        self._ws, self._stamp, self._kernel, self._held = ws, stamp, k, kernel
         return ws, k
 
     def run(self, kernel: torch.Tensor, waveform: torch.Tensor) -> torch.Tensor:

@@ -305,6 +305,8 @@ def _features(kind: str, rows: Tensor, o: dict) -> Tensor:
             finish = mat.to(torch.float32).contiguous()
         plan = _KaldiPlan(dev, window, padded, shift, bool(o.get("use_power", True)) if mel else True, banks, finish)
         _PLANS[key] = plan
+        if len(_PLANS) > 32:  # bounded: drop the oldest plan (dict preserves insertion order)
+            _PLANS.pop(next(iter(_PLANS)))
 
     # where the kernel puts things: [energy |] values, or values [| energy]
     if kind == "spectrogram":

@@ -644,7 +644,7 @@ int validate_desc(const b200a_frontend_desc* d) {
   if (d->n_fft < 2 || d->hop < 1 || d->win_length < 1 || d->win_length > d->n_fft || d->pad < 0) return B200A_EINVAL;
   if (d->n_fft > kMaxFft) return B200A_EUNSUPPORTED;
   if (d->pad_mode < B200A_PAD_REFLECT || d->pad_mode > B200A_PAD_CIRCULAR) return B200A_EINVAL;
-  if (d->n_mels < 0 || d->n_mfcc < 0 || d->n_mfcc > d->n_mels) return B200A_EINVAL;
+  if (d->n_mels < 0 || d->n_mfcc < 0 || (d->n_mfcc > 0 && d->n_mels == 0)) return B200A_EINVAL;  // LFCC allows n_lfcc > n_filter
   if (d->n_mels > 0 && !d->onesided) return B200A_EINVAL;
   return B200A_OK;
 }

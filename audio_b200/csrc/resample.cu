@@ -17,9 +17,22 @@
 //
 // Fallback (resample_direct_kernel): one output per thread over the phase's live taps, for ratios whose
 // tables or tiles do not fit (new' > 1024, orig' > ~1100) or mis-aligned inputs.
+//
+// Preferred kernel for odd orig' (resample_simt_kernel, e.g. 44.1 -> 16 kHz): the pruned FIR is only ~68 flop per
+// output sample, far below what keeps the legacy tensor path busy with error-compensated TF32 (3 MMAs per tile,
+// "math pipe throttle" in profiles/r1_resample_v4.txt), so it runs as a register-tiled FP32 product on packed
+// FFMA2 instead: a thread owns ONE frame of each of two adjacent 32-frame half-chunks x a group of 8 phases,
+// lanes are consecutive frames (stride orig' words: conflict-free for odd orig'), the 8 taps of a step are one
+// 32-byte broadcast read, and the two frames ride in the two halves of an f32x2 register pair:
+//     acc[q] (frame a | frame b) += (x_a[i] | x_b[i]) * tap[q][i]      (FFMA2 with a scalar-broadcast operand)
+// Half-chunks stream through a 3-slot ring of bulk asynchronous copies.  Step s pairs half-chunks (s-1, s) and
+// handles the phase groups of parity s & 1, so every half-chunk meets both parities (once as the newer, once as
+// the older member of a pair) and a slot is free for the next copy as soon as its second step ends.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
+#include "f32x2.cuh"
 #include "ptx.cuh"
 
 namespace b200a {
@@ -41,12 +54,20 @@ struct RsTile {  // one group of 8 phases
 struct RsHeader {
   uint32_t magic;
   int32_t orig_r, new_r, width, taps, max_support, n_tiles, total_steps;
-  int32_t reserved[8];
+  int32_t simt_tap_floats;  // size of the SIMT tap table (floats)
+  int32_t reserved[7];
 };
 static_assert(sizeof(RsHeader) == 64, "header is 64 bytes");
 
 struct RsLayout {
-  size_t header, support, tiles, frags, total;
+  size_t header, support, tiles, frags, sgroups, staps, total;
+};
+
+struct RsSimtGroup {  // one group of 8 phases for the SIMT kernel
+  int base;  // first tap (xp-relative) any phase of the group uses
+  int len;   // taps visited (multiple of 8; zero padded)
+  int off;   // float offset of the group's [len][8] tap block in the tap table
+  int pad;
 };
 
 inline int rs_tiles(int new_r) { return (new_r + 7) / 8; }
@@ -63,6 +84,10 @@ inline RsLayout rs_layout(int new_r, int taps) {
   l.frags = off;  // worst case: every group spans every tap
   const size_t nt = rs_tiles(new_r) <= kRsMaxTiles ? rs_tiles(new_r) : 0;
   off = align_up(off + sizeof(float4) * 32 * nt * ((size_t)taps / 8 + 2), 256);
+  l.sgroups = off;
+  off = align_up(off + sizeof(RsSimtGroup) * (size_t)rs_tiles(new_r), 256);
+  l.staps = off;  // worst case: every group spans every tap
+  off = align_up(off + sizeof(float) * 8 * (size_t)rs_tiles(new_r) * ((size_t)taps + 8), 256);
   l.total = off;
   return l;
 }
@@ -322,6 +347,241 @@ __global__ void __launch_bounds__(kRsMaxWarps * 32, 1) resample_mma_kernel(const
   }
 }
 
+// ---- SIMT kernel tables: per group of 8 phases the union of their live taps, zero padded to a multiple of 8,
+// stored tap-major ([i][8 phases]) so one step's taps are one 32-byte broadcast read.
+__global__ void resample_simt_plan_kernel(const float* __restrict__ kernel, const int2* __restrict__ support, int new_r,
+                                          int taps, int n_groups, RsHeader* hdr, RsSimtGroup* groups, float* table) {
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int g = 0; g < n_groups; ++g) {
+      int lo = taps, hi = 0;
+      for (int j = 8 * g; j < min(8 * g + 8, new_r); ++j) {
+        const int2 sp = support[j];
+        if (sp.y > 0) { lo = min(lo, sp.x); hi = max(hi, sp.x + sp.y); }
+      }
+      RsSimtGroup sg{0, 0, acc, 0};
+      if (hi > lo) {
+        sg.base = lo;
+        sg.len = (hi - lo + 7) & ~7;
+      }
+      groups[g] = sg;
+      acc += sg.len * 8;
+    }
+    hdr->simt_tap_floats = acc;
+  }
+  __syncthreads();
+  for (int g = 0; g < n_groups; ++g) {
+    const RsSimtGroup sg = groups[g];
+    for (int e = threadIdx.x; e < sg.len * 8; e += blockDim.x) {
+      const int i = e >> 3, q = e & 7, j = 8 * g + q, t = sg.base + i;
+      float v = 0.f;
+      if (j < new_r && t < taps) {
+        const int2 sp = support[j];
+        if (t >= sp.x && t < sp.x + sp.y) v = kernel[(size_t)j * taps + t];
+      }
+      table[sg.off + e] = v;
+    }
+  }
+}
+
+struct RsSimtParams {
+  const float* wave;
+  int64_t rows, length, row_stride;
+  float* out;
+  int64_t out_row_stride, out_len;
+  const RsHeader* hdr;
+  const RsSimtGroup* groups;
+  const float* table;
+  int orig_r, new_r, width, n_groups;
+  int tap_floats;        // shared memory granted to the tap table (floats)
+  int64_t frames;        // output frames per row
+  int64_t halves;        // 32-frame half-chunks per row
+  int64_t total_halves;  // rows * halves
+  int slot_floats;       // floats per ring slot
+  int out_vec;           // 1: every frame's 8-phase run may be stored as two float4
+};
+
+constexpr int kSimtMaxWarps = 12;
+
+// Stage the samples of half-chunk (row, hk) into a ring slot: xs[q] = xp[32 hk orig' + q - shift] with
+// xp[m] = x[m - width] (zero outside the signal).  Same alignment rule as rs_fill.
+__device__ __forceinline__ int simt_fill(const RsSimtParams& p, int64_t row, int64_t hk, float* xs, uint64_t* bar,
+                                         int tid, int nthreads) {
+  const int64_t T0 = hk * 32 * p.orig_r - p.width;
+  const float* x = p.wave + row * p.row_stride;
+  const int a0 = (int)((reinterpret_cast<uintptr_t>(x) >> 2) & 3);
+  const int shift = (int)((((a0 + T0) % 4) + 4) % 4);
+  const int64_t span = (int64_t)32 * p.orig_r + 2 * p.width;
+  const int64_t lo = T0 < 0 ? 0 : T0;
+  int64_t hi = T0 + span;
+  if (hi > p.length) hi = p.length;
+  if (hi < lo) hi = lo;
+  const int64_t lo_a = lo + ((4 - ((a0 + lo) & 3)) & 3);
+  const int64_t hi_a = hi - ((a0 + hi) & 3);
+  const int q_lo = (int)(lo - T0) + shift, q_hi = (int)(hi - T0) + shift;
+  if (q_lo > 0 && T0 < 0)
+    for (int q = tid; q < q_lo; q += nthreads) xs[q] = 0.f;
+  if (hi < T0 + span)
+    for (int q = q_hi + tid; q < p.slot_floats; q += nthreads) xs[q] = 0.f;
+  if (hi_a > lo_a) {
+    const int head = (int)(lo_a - lo), tail = (int)(hi - hi_a);
+    if (tid < head) xs[q_lo + tid] = x[lo + tid];
+    else if (tid >= 32 && tid < 32 + tail) xs[(int)(hi_a - T0) + shift + (tid - 32)] = x[hi_a + (tid - 32)];
+  } else {
+    for (int q = q_lo + tid; q < q_hi; q += nthreads) xs[q] = x[T0 + q - shift];
+  }
+  if (tid == 0) {
+    if (hi_a > lo_a) {
+      const uint32_t bytes = (uint32_t)(hi_a - lo_a) * 4u;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(xs + (lo_a - T0) + shift, x + lo_a, bytes, bar);
+    } else {
+      mbar_arrive(bar);
+    }
+  }
+  return shift;
+}
+// where sample xp[32 hk orig'] of half-chunk (row, hk) sits in its slot (simt_fill's `shift`)
+__device__ __forceinline__ int simt_shift(const RsSimtParams& p, int64_t row, int64_t hk) {
+  const int64_t T0 = hk * 32 * p.orig_r - p.width;
+  const int a0 = (int)((reinterpret_cast<uintptr_t>(p.wave + row * p.row_stride) >> 2) & 3);
+  return (int)((((a0 + T0) % 4) + 4) % 4);
+}
+
+__global__ void __launch_bounds__(kSimtMaxWarps * 32, 1) resample_simt_kernel(const RsSimtParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_x = reinterpret_cast<float*>(smem_raw);                                   // [3][slot_floats]
+  float* s_taps = s_x + 3 * (size_t)p.slot_floats;                                   // [tap_floats]
+  RsSimtGroup* s_groups = reinterpret_cast<RsSimtGroup*>(s_taps + ((p.tap_floats + 3) & ~3));  // [n_groups]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_groups + p.n_groups);              // [3]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+  const int tap_need = p.hdr->simt_tap_floats;
+  const bool taps_in_smem = tap_need <= p.tap_floats;
+  if (taps_in_smem)
+    for (int i = tid; i < tap_need; i += blockDim.x) s_taps[i] = p.table[i];
+  for (int i = tid; i < p.n_groups; i += blockDim.x) s_groups[i] = p.groups[i];
+  if (tid < 3) mbar_init(s_bar + tid, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  // this CTA's contiguous run of half-chunks [h0, h1) in (row, half) order
+  const int64_t h0 = p.total_halves * blockIdx.x / gridDim.x, h1 = p.total_halves * (blockIdx.x + 1) / gridDim.x;
+  if (h0 >= h1) return;
+  uint32_t phase_bits = 0;  // bit i: parity the next wait on slot i expects
+  {
+    const int64_t row = h0 / p.halves;
+    simt_fill(p, row, h0 - row * p.halves, s_x + (size_t)(h0 % 3) * p.slot_floats, s_bar + (h0 % 3), tid, blockDim.x);
+  }
+  __syncthreads();
+  const bool vec_ok = p.out_vec != 0;
+  for (int64_t s = h0; s <= h1; ++s) {
+    const int slot_hi = (int)(s % 3), slot_lo = (int)((s + 2) % 3), slot_nx = (int)((s + 1) % 3);
+    if (s + 1 < h1) {  // the slot of half-chunk s - 2: its last readers left at the barrier that ended step s - 1
+      const int64_t nrow = (s + 1) / p.halves;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      simt_fill(p, nrow, (s + 1) - nrow * p.halves, s_x + (size_t)slot_nx * p.slot_floats, s_bar + slot_nx, tid,
+                blockDim.x);
+    }
+    const bool has_hi = s < h1, has_lo = s > h0;
+    if (has_hi) {
+      mbar_wait(s_bar + slot_hi, (phase_bits >> slot_hi) & 1u);
+      phase_bits ^= 1u << slot_hi;
+    }
+    // frames of this thread: lane of the older half-chunk (s - 1) and lane of the newer one (s)
+    const int64_t hb = has_hi ? s : s - 1, ha = has_lo ? s - 1 : s;  // an absent side mirrors the present one
+    const int64_t row_a = ha / p.halves, row_b = hb / p.halves;
+    const int64_t fa = (ha - row_a * p.halves) * 32 + lane, fb = (hb - row_b * p.halves) * 32 + lane;
+    const float* xa = s_x + (size_t)(has_lo ? slot_lo : slot_hi) * p.slot_floats +
+                      simt_shift(p, row_a, ha - row_a * p.halves) + lane * p.orig_r;
+    const float* xb = s_x + (size_t)(has_hi ? slot_hi : slot_lo) * p.slot_floats +
+                      simt_shift(p, row_b, hb - row_b * p.halves) + lane * p.orig_r;
+    const bool st_a = has_lo && fa < p.frames, st_b = has_hi && fb < p.frames;
+    float* oa = p.out + row_a * p.out_row_stride + fa * p.new_r;
+    float* ob = p.out + row_b * p.out_row_stride + fb * p.new_r;
+    const int64_t na = fa * p.new_r, nb = fb * p.new_r;  // output index of phase 0 of the two frames
+    for (int g = 2 * warp + (int)(s & 1); g < p.n_groups; g += 2 * n_warps) {
+      const RsSimtGroup sg = s_groups[g];
+      const float* ta = xa + sg.base;
+      const float* tb = xb + sg.base;
+      uint64_t acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0ull;
+      auto fir = [&](auto in_smem) {
+        const float4* tp = reinterpret_cast<const float4*>((decltype(in_smem)::value ? s_taps : p.table) + sg.off);
+        // software pipelined over blocks of 4 taps: the loads of block k + 1 are in flight while block k is multiplied
+        float4 tq[2][8];
+        float va[2][4], vb[2][4];
+        auto load = [&](auto bi, int i4) {
+          constexpr int B = decltype(bi)::value;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            va[B][u] = ta[i4 + u];
+            vb[B][u] = tb[i4 + u];
+            if constexpr (decltype(in_smem)::value) {
+              tq[B][2 * u] = tp[2 * (i4 + u)];
+              tq[B][2 * u + 1] = tp[2 * (i4 + u) + 1];
+            } else {
+              tq[B][2 * u] = __ldg(tp + 2 * (i4 + u));
+              tq[B][2 * u + 1] = __ldg(tp + 2 * (i4 + u) + 1);
+            }
+          }
+        };
+        auto mac = [&](auto bi) {
+          constexpr int B = decltype(bi)::value;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint64_t xx = pk2(va[B][u], vb[B][u]);
+            const float4 t0 = tq[B][2 * u], t1 = tq[B][2 * u + 1];
+            acc[0] = fma2_raw(xx, pk2(t0.x, t0.x), acc[0]);
+            acc[1] = fma2_raw(xx, pk2(t0.y, t0.y), acc[1]);
+            acc[2] = fma2_raw(xx, pk2(t0.z, t0.z), acc[2]);
+            acc[3] = fma2_raw(xx, pk2(t0.w, t0.w), acc[3]);
+            acc[4] = fma2_raw(xx, pk2(t1.x, t1.x), acc[4]);
+            acc[5] = fma2_raw(xx, pk2(t1.y, t1.y), acc[5]);
+            acc[6] = fma2_raw(xx, pk2(t1.z, t1.z), acc[6]);
+            acc[7] = fma2_raw(xx, pk2(t1.w, t1.w), acc[7]);
+          }
+        };
+        using B0 = std::integral_constant<int, 0>;
+        using B1 = std::integral_constant<int, 1>;
+        if (sg.len > 0) load(B0{}, 0);
+#pragma unroll 1
+        for (int i8 = 0; i8 < sg.len; i8 += 8) {  // len is a multiple of 8
+          load(B1{}, i8 + 4);
+          mac(B0{});
+          if (i8 + 8 < sg.len) load(B0{}, i8 + 8);
+          mac(B1{});
+        }
+      };
+      if (taps_in_smem) fir(std::true_type{});
+      else fir(std::false_type{});
+      float ya[8], yb[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float2 v = upk2(acc[q]);
+        ya[q] = v.x;
+        yb[q] = v.y;
+      }
+      const int j0 = 8 * g;
+      const bool full = j0 + 8 <= p.new_r && vec_ok;
+      auto store = [&](float* o, int64_t n0, const float (&y)[8]) {
+        if (full && n0 + j0 + 8 <= p.out_len) {
+          *reinterpret_cast<float4*>(o + j0) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(o + j0 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (j0 + q < p.new_r && n0 + j0 + q < p.out_len) o[j0 + q] = y[q];
+        }
+      };
+      if (st_a) store(oa, na, ya);
+      if (st_b) store(ob, nb, yb);
+    }
+    __syncthreads();  // every reader of slot_lo is done: the next step's copy may overwrite it
+  }
+}
+
 // Straightforward one-output-per-thread kernel (any ratio).  Consecutive threads are consecutive
 // output samples, i.e. consecutive phases of the same input neighbourhood: input loads hit L1.
 __global__ void __launch_bounds__(256)
@@ -366,6 +626,9 @@ int resample_prepare_impl(const float* kernel, int orig_r, int new_r, int width,
     resample_plan_kernel<<<1, 256, 0, stream>>>(kernel, support, new_r, taps, rs_tiles(new_r), hdr,
                                                 reinterpret_cast<RsTile*>(base + l.tiles),
                                                 reinterpret_cast<float4*>(base + l.frags));
+  resample_simt_plan_kernel<<<1, 256, 0, stream>>>(kernel, support, new_r, taps, rs_tiles(new_r), hdr,
+                                                   reinterpret_cast<RsSimtGroup*>(base + l.sgroups),
+                                                   reinterpret_cast<float*>(base + l.staps));
   return launch_status();
 }
 
@@ -379,12 +642,70 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
   const RsLayout l = rs_layout(new_r, taps);
   const unsigned char* base = static_cast<const unsigned char*>(ws);
 
+  // B200A_RS=simt|mma|direct forces one kernel family (A/B measurements, tests); default: the first that applies
+  static const int forced = [] {
+    const char* e = std::getenv("B200A_RS");
+    if (e == nullptr) return 0;
+    return e[0] == 's' ? 1 : (e[0] == 'm' ? 2 : (e[0] == 'd' ? 3 : 0));
+  }();
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return B200A_ECUDA;
+
+  // ---- packed-FP32 SIMT path: odd orig' (conflict-free frame-per-lane reads) and the 3-slot ring fits -------------
+  {
+    const int n_groups = rs_tiles(new_r);
+    const int slot_floats = (32 * orig_r + 2 * width + 3 + 8 + 3) & ~3;  // span + alignment shift + zero-tap over-read
+    const size_t ring_bytes = sizeof(float) * 3 * (size_t)slot_floats;
+    const size_t fixed = ring_bytes + sizeof(RsSimtGroup) * (size_t)n_groups + 64;
+    const bool want = forced == 1 || (forced == 0 && (orig_r & 1) == 1 && n_groups >= 4);
+    if (want && fixed + 8192 <= (size_t)227 * 1024 && (reinterpret_cast<uintptr_t>(wave) & 3) == 0 &&
+        length + (int64_t)taps + 64 * (int64_t)orig_r < ((int64_t)1 << 31)) {
+      RsSimtParams p{};
+      p.wave = wave;
+      p.rows = rows;
+      p.length = length;
+      p.row_stride = row_stride;
+      p.out = out;
+      p.out_row_stride = out_row_stride;
+      p.out_len = out_len;
+      p.hdr = reinterpret_cast<const RsHeader*>(base + l.header);
+      p.groups = reinterpret_cast<const RsSimtGroup*>(base + l.sgroups);
+      p.table = reinterpret_cast<const float*>(base + l.staps);
+      p.orig_r = orig_r;
+      p.new_r = new_r;
+      p.width = width;
+      p.n_groups = n_groups;
+      p.frames = (out_len + new_r - 1) / new_r;
+      p.halves = (p.frames + 31) / 32;
+      p.total_halves = rows * p.halves;
+      p.slot_floats = slot_floats;
+      p.out_vec = (new_r % 4 == 0 && out_row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+      // the tap table gets whatever shared memory is left (the kernel compares the device-side size written by
+      // prepare with this room and reads the table through L1 instead when it does not fit)
+      const size_t tap_cap = sizeof(float) * 8 * (size_t)n_groups * ((size_t)taps + 8);
+      const size_t room = ((size_t)227 * 1024 - fixed) & ~(size_t)15;
+      p.tap_floats = (int)((tap_cap < room ? tap_cap : room) / sizeof(float));
+      const size_t smem = fixed + sizeof(float) * (size_t)p.tap_floats;
+      if (cudaFuncSetAttribute(resample_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        return B200A_ECUDA;
+      int warps = (n_groups + 1) / 2;  // one phase group of the step's parity per warp
+      if (warps > kSimtMaxWarps) warps = kSimtMaxWarps;
+      if (warps < 4) warps = 4;
+      int64_t grid = p.total_halves < sms ? p.total_halves : sms;
+      if (grid < 1) grid = 1;
+      resample_simt_kernel<<<(unsigned)grid, warps * 32, smem, stream>>>(p);
+      return launch_status();
+    }
+    if (forced == 1) return B200A_EUNSUPPORTED;
+  }
+
   // ---- tensor-pipe path -------------------------------------------------------------------------
   const int n_tiles = rs_tiles(new_r);
   const int xs_floats = (kRsFrames * orig_r + taps + 8 + 4 + 3) & ~3;
   const size_t smem_fixed = sizeof(float) * 2 * (size_t)xs_floats + 16 + sizeof(RsTile) * ((n_tiles + 3) & ~3);
   const bool aligned = (reinterpret_cast<uintptr_t>(wave) & 3) == 0;  // any float pointer; rows may have any pitch
-  if (n_tiles <= kRsMaxTiles && aligned && smem_fixed + 1024 <= (size_t)kRsSmemBudget) {
+  if (forced != 3 && n_tiles <= kRsMaxTiles && aligned && smem_fixed + 1024 <= (size_t)kRsSmemBudget) {
     RsParams p{};
     p.wave = wave;
     p.rows = rows;
@@ -411,10 +732,6 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
     const size_t smem = smem_fixed + p.frag_smem_bytes;
     if (cudaFuncSetAttribute(resample_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess)
-      return B200A_ECUDA;
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
       return B200A_ECUDA;
     int64_t grid = p.total_blocks < sms ? p.total_blocks : sms;
     if (grid < 1) grid = 1;

@@ -11,6 +11,7 @@ Differences, all explicit (never a silent fallback): CUDA float32 tensors only, 
 """
 from __future__ import annotations
 
+import collections
 import math
 import warnings
 from typing import Optional, Union
@@ -105,15 +106,18 @@ def spectrogram(
 
 
 # ---- inverse spectrogram ------------------------------------------------------------------------------------
-_ENVELOPE_OK = {}
+_ENVELOPE_OK: "collections.OrderedDict[tuple, Tensor]" = collections.OrderedDict()
+_ENVELOPE_CACHE_SIZE = 64
 
 
 def _check_window_envelope(window: Tensor, n_fft: int, win_length: int, hop: int, frames: int, start: int, end: int) -> None:
     """torch.istft refuses windows whose overlap-added square dips below 1e-11 inside the returned range
     ("window overlap add min"); it finds out with a device synchronisation, and so does this check -- once per
-    (window contents, geometry), cached."""
+    (window tensor, geometry).  The cache entry HOLDS the window tensor, so its (data_ptr, _version) key cannot
+    be matched by a different window that was handed the recycled allocation; the cache is a bounded LRU."""
     key = (window.data_ptr(), window._version, str(window.device), n_fft, win_length, hop, frames, start, end)
     if key in _ENVELOPE_OK:
+        _ENVELOPE_OK.move_to_end(key)
         return
     import numpy as np
 
@@ -121,13 +125,16 @@ def _check_window_envelope(window: Tensor, n_fft: int, win_length: int, hop: int
     left = (n_fft - win_length) // 2
     w[left:left + win_length] = window.detach().double().cpu().numpy()
     expected = n_fft + hop * (frames - 1)
+    # overlap-added w^2 without a Python loop over frames: scatter-add over the (frames, n_fft) index grid
     env = np.zeros(expected)
-    for t in range(frames):
-        env[t * hop:t * hop + n_fft] += w * w
+    idx = (np.arange(frames)[:, None] * hop + np.arange(n_fft)[None, :]).ravel()
+    np.add.at(env, idx, np.tile(w * w, frames))
     seg = env[start:min(end, expected)]
     if seg.size and np.abs(seg).min() < 1e-11:
         raise RuntimeError("istft(...) window overlap add min: 1 (the window envelope is zero inside the output range)")
-    _ENVELOPE_OK[key] = True
+    _ENVELOPE_OK[key] = window
+    if len(_ENVELOPE_OK) > _ENVELOPE_CACHE_SIZE:
+        _ENVELOPE_OK.popitem(last=False)
 
 
 def inverse_spectrogram(
@@ -433,12 +440,21 @@ def mfcc(
     else:
         rows_per_group, gmax = 1, None
     feat = plan.run(ws, _lib.STAGE_FEAT, waveform, gmax, rows_per_group)
-    if clamp and process_group is not None and waveform.dim() <= 2:
+    if clamp and waveform.dim() <= 2:
+        gmax = _exchange_group_max(gmax, process_group)
+    out = plan.mfcc_finish(ws, feat, gmax, rows_per_group, top_db if clamp else None)
+    return _unpack(out, waveform)
+
+
+def _exchange_group_max(gmax: Tensor, process_group) -> Tensor:
+    """The path's only cross-rank message: all-reduce(MAX) of the running dB maximum of a 2-D batch that is sharded
+    over ``process_group`` (reference semantics: ONE ``amax`` over the whole batch, functional.py:395-399).
+    In place; a ``None`` group (single process) is the identity."""
+    if process_group is not None:
         import torch.distributed as dist
 
         dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=process_group)
-    out = plan.mfcc_finish(ws, feat, gmax, rows_per_group, top_db if clamp else None)
-    return _unpack(out, waveform)
+    return gmax
 
 
 # ---- resampling ---------------------------------------------------------------------------------

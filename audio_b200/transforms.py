@@ -584,6 +584,24 @@ class PitchShift(torch.nn.Module):
         self.kernel = None
         self._plan = None
 
+    # The reference keeps ``kernel`` as a lazily materialised parameter, so its state_dict carries a "kernel" entry
+    # once the module has run (_transforms.py:1731-1757).  Mirror that: emit the taps when they exist, accept them on load.
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        if self.kernel is not None:
+            destination[prefix + "kernel"] = self.kernel if keep_vars else self.kernel.detach()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        k = state_dict.pop(prefix + "kernel", None)
+        if isinstance(k, Tensor) and k.numel() > 0:
+            orig_r = self.orig_freq // self.gcd
+            taps = k.shape[-1]
+            if k.dim() == 3 and k.shape[0] == self.sample_rate // self.gcd and taps > orig_r and (taps - orig_r) % 2 == 0:
+                self.kernel, self.width, self._plan = k.detach().clone(), (taps - orig_r) // 2, None
+            else:
+                error_msgs.append(f"size mismatch for {prefix}kernel: {tuple(k.shape)} does not fit this PitchShift")
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
     def forward(self, waveform: Tensor) -> Tensor:
         shape = waveform.size()
         flat = waveform.reshape(-1, shape[-1])
@@ -595,9 +613,13 @@ class PitchShift(torch.nn.Module):
         stretched = F.inverse_spectrogram(spec_stretch, int(round(ori_len / rate)), 0, self.window, self.n_fft,
                                           self.hop_length, self.win_length, False)
         if self.orig_freq != self.sample_rate:
-            if self.kernel is None or self.kernel.device != waveform.device:
+            if self.kernel is None:
                 self.kernel, self.width = F._get_sinc_resample_kernel(
                     self.orig_freq, self.sample_rate, self.gcd, dtype=waveform.dtype, device=waveform.device)
+                self._plan = None
+            elif self.kernel.device != waveform.device or self.kernel.dtype != waveform.dtype:  # loaded / moved
+                self.kernel, self._plan = self.kernel.to(device=waveform.device, dtype=waveform.dtype), None
+            if self._plan is None:
                 self._plan = ResamplePlan(self.orig_freq // self.gcd, self.sample_rate // self.gcd, self.width)
             shifted = F._apply_sinc_resample_kernel(stretched, self.orig_freq, self.sample_rate, self.gcd, self.kernel,
                                                     self.width, self._plan)

@@ -3,8 +3,8 @@
 The hot path shards by utterance with no collective, except MFCC's batch-global top_db cut-off
 (reference functional.py:395-399) which needs ONE all-reduce(MAX) of a scalar between the
 feature kernel and the clamp+DCT kernel (audio_b200.functional.mfcc, `process_group`).
-Here each rank runs the ORACLE (as a stand-in for its GPU) on its shard, follows exactly that
-protocol with torch.distributed, and rank 0 checks the re-assembled result against the oracle on
+Here each rank runs the ORACLE (as a stand-in for its GPU kernels) on its shard, exchanges the maximum with the
+product's own `_exchange_group_max`, and rank 0 checks the re-assembled result against the oracle on
 the whole batch -- including the property that skipping the all-reduce gives a different answer.
 """
 import os
@@ -45,9 +45,12 @@ def _worker(rank, world, port, out_path):
         mel = O.mel_spectrogram(shard, sample_rate=16000, **kw)
         feat = O.amplitude_to_db(mel, 10.0, 1e-10, 0.0, None)
         local_max = torch.tensor([feat.max()], dtype=torch.float32)
-        # the one collective of the path
-        global_max = local_max.clone()
-        dist.all_reduce(global_max, op=dist.ReduceOp.MAX)
+        # the one collective of the path -- through the product's own function (audio_b200.functional.mfcc calls it
+        # between the feature kernel and the clamp + DCT kernel)
+        from audio_b200.functional import _exchange_group_max
+
+        global_max = _exchange_group_max(local_max.clone(), dist.group.WORLD)
+        assert _exchange_group_max(local_max, None) is local_max  # no group: identity
         # stage 2: clamp at (global max - top_db), DCT
         dct = O.create_dct(13, 40, "ortho")
 

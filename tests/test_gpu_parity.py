@@ -138,19 +138,21 @@ def test_melspectrogram_scaled_rows_and_strides(ref_cases):
 
 
 def test_mfcc_reference_batch_coupling(ref_cases):
+    """MFCC against the reference's own outputs under the stated rule |a-e| <= 1e-4 |e| + 1e-4 rms(e).
+    The slack is pinned, not asserted: tests/test_oracle_golden.py::test_mfcc_tolerance_is_pinned shows the
+    reference's fp32 CPU run itself sits within 6 % of that bound from the fp64 oracle on these very cases."""
     kw = dict(n_fft=1024, hop_length=256, n_mels=80)
     mf = T.MFCC(16000, n_mfcc=40, melkwargs=kw).to(DEV)
     x, xs = dev(ref_cases["mel_in"]), dev(ref_cases["mel_scaled_in"])
-    tol = dict(rtol=1e-4, atol=5e-3)  # dB units (range ~[-100, 100]) summed over 80 mels
-    assert_close(host(mf(x)), ref_cases["mfcc_x_out"], **tol)
-    assert_close(host(mf(xs)), ref_cases["mfcc_2d_out"], **tol)  # ONE cut-off for the batch
-    assert_close(host(mf(xs[:, None, :])), ref_cases["mfcc_3d_out"], **tol)  # per-item cut-off
-    assert_close(host(mf(xs[0])), ref_cases["mfcc_1d_out"], **tol)
+    scaled_tol_close(host(mf(x)), ref_cases["mfcc_x_out"], what="mfcc_x")
+    scaled_tol_close(host(mf(xs)), ref_cases["mfcc_2d_out"], what="mfcc_2d")  # ONE cut-off for the batch
+    scaled_tol_close(host(mf(xs[:, None, :])), ref_cases["mfcc_3d_out"], what="mfcc_3d")  # per-item cut-off
+    scaled_tol_close(host(mf(xs[0])), ref_cases["mfcc_1d_out"], what="mfcc_1d")
     mfl = T.MFCC(16000, n_mfcc=13, log_mels=True, melkwargs=dict(n_fft=400, hop_length=160, n_mels=23)).to(DEV)
-    assert_close(host(mfl(x)), ref_cases["mfcc_log_out"], rtol=1e-4, atol=2e-3)
+    scaled_tol_close(host(mfl(x)), ref_cases["mfcc_log_out"], what="mfcc_log")
     mfn = T.MFCC(16000, n_mfcc=20, norm=None, melkwargs=dict(n_fft=512, hop_length=256, n_mels=64)).to(DEV)
-    assert_close(host(mfn(x)), ref_cases["mfcc_nonorm_out"], rtol=1e-4, atol=5e-2)
-    assert_close(host(T.MFCC().to(DEV)(x)), ref_cases["mfcc_default_out"], **tol)
+    scaled_tol_close(host(mfn(x)), ref_cases["mfcc_nonorm_out"], what="mfcc_nonorm")
+    scaled_tol_close(host(T.MFCC().to(DEV)(x)), ref_cases["mfcc_default_out"], what="mfcc_default")
 
 
 def test_amplitude_to_db_reference(ref_cases):
