@@ -10,7 +10,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import _lib
+from . import _lib, _ops
 from ._bookkeeping import resample_len
 
 
@@ -32,6 +32,11 @@ def _no_autograd(t: torch.Tensor) -> None:
             "audio_b200 kernels are forward-only: the input requires grad. Call under torch.no_grad() / "
             "torch.inference_mode(), or detach() the input."
         )
+
+
+def _version_of(t: torch.Tensor) -> int:
+    """In-place edit counter of a tensor; inference tensors (created under torch.inference_mode) keep none."""
+    return -1 if t.is_inference() else t._version
 
 
 def _stream_ptr(device: torch.device) -> int:
@@ -58,6 +63,7 @@ class FrontendPlan:
         # the constant tensors the workspace was built from: holding them keeps their storage from being
         # recycled, so an equal (data_ptr, _version) stamp can only mean "the same, unmodified tensor"
         self._held = None
+        self._desc_lists = None  # the descriptor as (ints, floats) for the torch.library ops
 
     @staticmethod
     def make_desc(
@@ -88,7 +94,7 @@ class FrontendPlan:
         return d
 
     def _stamp_of(self, *tensors):
-        return tuple(None if t is None else (t.data_ptr(), t._version, str(t.device)) for t in tensors)
+        return tuple(None if t is None else (t.data_ptr(), _version_of(t), str(t.device)) for t in tensors)
 
     def workspace(self, window: torch.Tensor, fb: Optional[torch.Tensor], dct: Optional[torch.Tensor]) -> torch.Tensor:
         """Return a prepared workspace, rebuilding it if any constant buffer changed."""
@@ -157,51 +163,19 @@ class FrontendPlan:
             )
         n_bins = lib.b200a_num_bins(d.n_fft, d.onesided)
         width = d.n_mels if stage >= _lib.STAGE_MEL else n_bins
-        shape = (rows, frames, width, 2) if stage == _lib.STAGE_COMPLEX else (rows, frames, width)
-        dev = waveform.device
-        with torch.cuda.device(dev):
-            out = torch.empty(shape, dtype=torch.float32, device=dev)
-            rc = lib.b200a_frontend_run(
-                d,
-                ws.data_ptr(),
-                stage,
-                flat.data_ptr(),
-                rows,
-                length,
-                stride,
-                out.data_ptr(),
-                None if group_max is None else group_max.data_ptr(),
-                rows_per_group,
-                _stream_ptr(dev),
-            )
-        if rc == _lib.ESHORT:
-            raise RuntimeError(
-                f"audio_b200: padding size n_fft//2={d.n_fft // 2} should be less than the input length "
-                f"{length + 2 * d.pad} for pad_mode reflect/circular (torch.stft raises the same way)"
-            )
-        _lib.check(rc, "frontend_run")
-        return out
+        # through the dispatcher (b200audio::frontend_run, audio_b200/_ops.py): allocates `out`, launches on the
+        # current stream of the waveform's device, raises on a negative status
+        desc_i, desc_f = self._packed_desc()
+        return _ops.frontend_run(flat, ws, desc_i, desc_f, stage, frames, width, stride, group_max, rows_per_group)
 
     def mfcc_finish(self, ws, feat, group_max, rows_per_group: int, top_db: Optional[float]) -> torch.Tensor:
-        lib = _lib.lib()
-        rows, frames, _ = feat.shape
-        dev = feat.device
-        with torch.cuda.device(dev):
-            out = torch.empty((rows, frames, self.desc.n_mfcc), dtype=torch.float32, device=dev)
-            rc = lib.b200a_mfcc_finish(
-                self.desc,
-                ws.data_ptr(),
-                feat.data_ptr(),
-                rows,
-                frames,
-                None if group_max is None else group_max.data_ptr(),
-                rows_per_group,
-                -1.0 if top_db is None else float(top_db),
-                out.data_ptr(),
-                _stream_ptr(dev),
-            )
-        _lib.check(rc, "mfcc_finish")
-        return out
+        desc_i, desc_f = self._packed_desc()
+        return _ops.mfcc_finish(feat, ws, desc_i, desc_f, group_max, rows_per_group, -1.0 if top_db is None else float(top_db))
+
+    def _packed_desc(self):
+        if self._desc_lists is None:
+            self._desc_lists = _ops.pack_desc(self.desc)
+        return self._desc_lists
 
 
 def new_group_max(groups: int, device: torch.device) -> torch.Tensor:
@@ -224,7 +198,7 @@ class ResamplePlan:
         self._held = None  # the kernel tensor behind the stamp (see FrontendPlan._held)
 
     def workspace(self, kernel: torch.Tensor):
-        stamp = (kernel.data_ptr(), kernel._version, str(kernel.device))
+        stamp = (kernel.data_ptr(), _version_of(kernel), str(kernel.device))
         if self._ws is not None and stamp == self._stamp:
             return self._ws, self._kernel
         _require_cuda_f32(kernel, "kernel")
@@ -255,13 +229,6 @@ class ResamplePlan:
         out_len = resample_len(length, self.orig_r, self.new_r)
         # the reference returns a view into (rows, frames*new') memory: keep that row pitch
         pitch = (length // self.orig_r + 1) * self.new_r
-        dev = waveform.device
-        with torch.cuda.device(dev):
-            buf = torch.empty((rows, pitch), dtype=torch.float32, device=dev)
-            rc = lib.b200a_resample_run(
-                ws.data_ptr(), k.data_ptr(), self.orig_r, self.new_r, self.width,
-                flat.data_ptr(), rows, length, stride, buf.data_ptr(), pitch, out_len, _stream_ptr(dev),
-            )
-        _lib.check(rc, "resample_run")
+        buf = _ops.resample_run(flat, ws, k, self.orig_r, self.new_r, self.width, stride, out_len, pitch)
         out = buf[:, :out_len]
         return out.view(waveform.shape[:-1] + (out_len,)) if rows > 0 else out.reshape(waveform.shape[:-1] + (out_len,))

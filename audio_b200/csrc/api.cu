@@ -88,6 +88,29 @@ int64_t b200a_resample_len(int64_t length, int32_t orig_r, int32_t new_r) {
   return (int64_t)std::ceil((float)q);
 }
 
+int b200a_resample_support(int32_t orig_r, int32_t new_r, int32_t lowpass_filter_width, double rolloff, int32_t phase,
+                           int32_t* first, int32_t* count) {
+  // functional.py:1376-1400: tap i of phase j is the windowed sinc at t = (-j/new' + (i - width)/orig') * base,
+  // clamped to +-lowpass_filter_width where the window is (numerically) zero: live taps have |t| < lpw.
+  if (orig_r < 1 || new_r < 1 || lowpass_filter_width < 1 || !(rolloff > 0.0) || phase < 0 || phase >= new_r ||
+      first == nullptr || count == nullptr)
+    return B200A_EINVAL;
+  const int32_t width = b200a_resample_width(orig_r, new_r, lowpass_filter_width, rolloff);
+  const int32_t taps = 2 * width + orig_r;
+  const double base = (double)(orig_r < new_r ? orig_r : new_r) * rolloff;
+  int32_t lo = taps, hi = -1;
+  for (int32_t i = 0; i < taps; ++i) {
+    const double t = ((double)(i - width) / (double)orig_r - (double)phase / (double)new_r) * base;
+    if (std::fabs(t) < (double)lowpass_filter_width) {
+      if (i < lo) lo = i;
+      hi = i;
+    }
+  }
+  *first = hi < 0 ? 0 : lo;
+  *count = hi < 0 ? 0 : hi - lo + 1;
+  return B200A_OK;
+}
+
 size_t b200a_frontend_workspace_bytes(const b200a_frontend_desc* desc) {
   if (validate_desc(desc) != B200A_OK) return 0;
   return ws_layout(*desc).total + pow2_workspace_extra(desc);

@@ -48,6 +48,7 @@ namespace b200a {
 
 namespace {
 
+constexpr int kDefaultSkewCycles = 0;  // start-up stagger between warps of one scheduler (B200A_SKEW overrides)
 constexpr float kKaldiEps = 1.1920928955078125e-07f;  // numeric_limits<float>::epsilon(), kaldi.py:21-22
 constexpr int kPadSymmetric = 4;  // internal pad mode: x[-1-j] = x[j], x[L+j] = x[L-1-j] (Kaldi snip_edges = false)
 constexpr int kWarps = 8;     // transform warps per CTA
@@ -212,6 +213,7 @@ struct Pow2Params {
   const unsigned char* tc_b;   // its banded bf16 B blocks
   int hop, pad, center, pad_mode, n_mels;
   int stage, log_mels, bulk_ok, stage_ok;
+  int skew_cycles;  // start-up stagger between the transform warps of one scheduler (see stagger_start)
   // output row geometry: value m of frame t goes to out[(row * frames + t) * out_width + out_col0 + m]
   int out_width, out_col0, out_vec;  // out_vec: floats every row start is aligned to (1, 2 or 4)
   // Kaldi framing / per-frame conditioning (compliance/kaldi.py:44-83, :153-216); kaldi == 0: torch.stft framing
@@ -272,6 +274,19 @@ __device__ __forceinline__ void reg_alloc() {
 template <int N>
 __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// The transform warps of a CTA run the same long sequence of phases (shared-memory loads, FP-dense register FFT,
+// transpose, FFT, shuffles, stores).  Started together they stay roughly in phase, so the warps sharing a scheduler all
+// want the FMA pipe at once and then all want the load/store pipe at once ("math pipe throttle" next to an FMA
+// pipe that is idle half of the time, profiles/r2_mel_v2.txt).  A one-time stagger at start-up -- warp w of
+// scheduler w % 4 waits (w / 4) * skew cycles -- puts them in different phases for the rest of the kernel.
+__device__ __forceinline__ void stagger_start(int warp, int skew_cycles) {
+  const long long wait = (long long)(warp >> 2) * skew_cycles;
+  if (wait > 0) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < wait) __nanosleep(64);
+  }
 }
 
 // Per-warp walker over this warp's units: (row, unit-in-row) of the current and the next unit,
@@ -612,6 +627,7 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_pow2_power_kernel(const Pow2P
     if (lane == 0) issue_bulk<G>(p, half, cur.row, cur.ub, stage, bar);
     staged = true;
   }
+  stagger_start(warp, p.skew_cycles);
   for (; cur.u < p.total_units; cur.advance()) {
     float pa[17], pb[17];
     transform_unit<POWER_MODE, G, HG, STAGE_IS_TILE, KALDI>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
@@ -1189,9 +1205,8 @@ struct TcGeo {
   static constexpr int kBBudget = ((227 * 1024 - kFixed) / 128) * 128;
   static_assert(kSteps <= kTcMaxSteps && kRows <= 64 && kRows % 8 == 0, "one M = 64 tile per iteration");
 };
-inline int tc_b_budget(int n_fft) {
-  return n_fft == 1024 ? TcGeo<32>::kBBudget : (n_fft == 512 ? TcGeo<16>::kBBudget : TcGeo<8>::kBBudget);
-}
+struct Tc2;
+int tc_b_budget(int n_fft);  // defined after Tc2
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -1287,6 +1302,7 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
     const int row_a = Ge::kFrames * warp + 2 * gi;  // even: rows a and a + 1 share the 8-row group
     const int lane_off = (l >> 3) * kStride + (row_a >> 3) * 256 + (row_a & 7) * 32 + (l & 7) * 4;
     constexpr int kStepM = (G / 8) * kStride;
+    stagger_start(warp, p.skew_cycles);
     int it = 0;
     for (int64_t base = u0; base < p.total_units; base += stride, ++it, cur.advance()) {
       const bool valid = cur.u < p.total_units;
@@ -1470,21 +1486,38 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
   }
 }
 
+// Position kp of the contraction's (permuted) K axis -> spectrum bin, or -1 for a padding position.
+//   perm_g == 0: identity (operand buffer in bin order; n_fft 256 / 512 body).
+//   perm_g == G: the n_fft = 32 G register FFT leaves lane l with bins l + G m; the transform warps publish the PAIR
+//                (m, m + 1) of a lane as one packed bf16x2 word, so K position 2 G (m >> 1) + 2 l + (m & 1) holds
+//                bin l + G m, and the Nyquist bin sits at position n_fft / 2.
+__host__ __device__ __forceinline__ int tc_bin_of(int kp, int perm_g, int n_bins) {
+  if (perm_g == 0) return kp < n_bins ? kp : -1;
+  const int half = 16 * perm_g;  // n_fft / 2
+  if (kp == half) return half;
+  if (kp > half) return -1;
+  const int j = kp / (2 * perm_g), rem = kp % (2 * perm_g);
+  return (rem >> 1) + perm_g * (2 * j + (rem & 1));
+}
+
 // Banded bf16 hi / lo UMMA B blocks and their step table.  One block.
 __global__ void prepare_tc_kernel(const float* __restrict__ fb, int n_bins, int n_mels, int n_fft, int budget,
-                                  TcPlan* plan, unsigned char* blocks) {
+                                  int perm_g, TcPlan* plan, unsigned char* blocks) {
   __shared__ int s_lo[kTcMaxSteps], s_hi[kTcMaxSteps];
   __shared__ TcPlan s_plan;
   const int k_steps = (n_fft / 16 + 2) / 2;  // (2 G + 2) / 2
   const int n_pad = (n_mels + 15) / 16 * 16;
   if ((int)threadIdx.x < k_steps) {
     int lo = n_mels, hi = -1;
-    for (int k = 16 * threadIdx.x; k < 16 * (int)threadIdx.x + 16 && k < n_bins; ++k)
+    for (int kp = 16 * threadIdx.x; kp < 16 * (int)threadIdx.x + 16; ++kp) {
+      const int k = tc_bin_of(kp, perm_g, n_bins);
+      if (k < 0) continue;
       for (int n = 0; n < n_mels; ++n)
         if (fb[(size_t)k * n_mels + n] != 0.f) {
           lo = min(lo, n);
           hi = max(hi, n);
         }
+    }
     s_lo[threadIdx.x] = lo;
     s_hi[threadIdx.x] = hi;
   }
@@ -1517,8 +1550,8 @@ __global__ void prepare_tc_kernel(const float* __restrict__ fb, int n_bins, int 
       const TcStep st = s_plan.step[s];
       for (int i = threadIdx.x; i < (int)st.n * 16; i += blockDim.x) {
         const int nl = i >> 4, kk = i & 15;
-        const int n = (int)st.col + nl, k = 16 * (int)st.kstep + kk;
-        const float v = (n < n_mels && k < n_bins) ? fb[(size_t)k * n_mels + n] : 0.f;
+        const int n = (int)st.col + nl, k = tc_bin_of(16 * (int)st.kstep + kk, perm_g, n_bins);
+        const float v = (n < n_mels && k >= 0) ? fb[(size_t)k * n_mels + n] : 0.f;
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(h));
         // operand row of filter nl: 16 (nl / 8) + nl % 8 for F_hi, + 8 for F_lo; 2 n rows x 16 B per k chunk
@@ -1533,6 +1566,276 @@ __global__ void prepare_tc_kernel(const float* __restrict__ fb, int n_bins, int 
     reinterpret_cast<int*>(plan)[i] = reinterpret_cast<const int*>(&s_plan)[i];
 }
 
+// ================================================================================================
+// n_fft = 1024 contraction, second generation (mel_body_tc2).  What changed against mel_body_tc:
+//   * the transform warps publish bf16 hi / lo words DIRECTLY (no fp32 staging, no conversion pass by other warps,
+//     one barrier hop less): a lane packs the powers of its bins (l + 32 m, l + 32 (m + 1)) into one bf16x2 word,
+//     which makes the contraction's K axis a permutation of the spectrum (tc_bin_of) -- the banded filterbank
+//     blocks are built in the same order, so nothing else notices;
+//   * the hi and lo planes of a frame are two ROWS of the same M = 64 operand tile (row group 2 (r / 8) = hi,
+//     + 1 = lo), so ONE tcgen05.mma per k-step produces P_hi F and P_lo F side by side in tensor memory lanes
+//     i and i + 8 of the frame group's lane quadrant, and the epilogue adds them with one shuffle.  Against two
+//     M = 64 instructions per k-step (each reading 64 operand rows of which 24 were real) this halves the
+//     tensor core's shared-memory reads: 48 of the 64 rows are real now.
+//   * the four service warps only issue MMAs (one of them) and run the epilogue (three: one per 8-frame group).
+// ================================================================================================
+struct Tc2 {
+  static constexpr int NW = 12;                       // transform warps
+  static constexpr int kThreads = (NW + kMelWarps) * 32;
+  static constexpr int kFftRegs = 144, kSvcRegs = 80;  // 384*144 + 128*80 = 65536
+  static constexpr int kRows = 2 * NW;                // frames per tile: 24
+  static constexpr int kQuads = (kRows + 7) / 8;      // 8-frame groups == TMEM lane quadrants in use == epilogue warps
+  static constexpr int kChunks = 66;                  // 8-position K chunks: 512 + Nyquist chunk + one of padding
+  static constexpr int kSteps = kChunks / 2;
+  static constexpr int kChunkStride = kQuads * 256 + 16;  // bytes: [hi 128 B | lo 128 B] per frame group; / 16 odd
+  static constexpr int kOperand = ((kChunks * kChunkStride + 1024 + 127) / 128) * 128;  // + the M = 64 over-read
+  static constexpr int kFixed = kOperand + 8 * (NW * Geo<32>::kTileF2 + 32 * 32) + 16 * kRows + 32 * kTcMaxSteps +
+                                8 * (NW + 8) + 16;
+  static constexpr int kBBudget = ((227 * 1024 - kFixed) / 128) * 128;
+  static_assert(kQuads <= 3 && (kChunkStride / 16) % 2 == 1 && kSteps <= kTcMaxSteps, "layout");
+  static_assert(kBBudget >= 40 * 1024, "banded filterbank blocks need room");
+};
+struct __align__(16) TcIssue2 {  // ready-to-issue descriptors of one k-step
+  uint64_t a, b;
+  uint32_t idesc, col, pad0, pad1;
+};
+
+template <int POWER_MODE, int HG, bool KALDI>
+__device__ __forceinline__ void mel_body_tc2(const Pow2Params& p, unsigned char* smem_raw) {
+  constexpr int G = 32;
+  using Ge = Geo<G>;
+  constexpr int NW = Tc2::NW, kRows = Tc2::kRows, kQuads = Tc2::kQuads, kStride = Tc2::kChunkStride;
+  unsigned char* s_a = smem_raw;                                                   // operand buffer
+  unsigned char* s_b = s_a + Tc2::kOperand;                                        // banded B blocks
+  float2* s_tile_all = reinterpret_cast<float2*>(s_b + Tc2::kBBudget);             // [NW][kTileF2]
+  float2* s_tw = s_tile_all + NW * Ge::kTileF2;                                    // [32][G]
+  int64_t* s_slot = reinterpret_cast<int64_t*>(s_tw + 32 * G);                     // [kRows] output offsets
+  int64_t* s_grp = s_slot + kRows;                                                 // [kRows] top_db groups
+  TcIssue2* s_issue = reinterpret_cast<TcIssue2*>(s_grp + kRows);                  // [kTcMaxSteps]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_issue + kTcMaxSteps);            // [NW] staging
+  uint64_t* s_full = s_bar + NW;                                                   // operand tile published
+  uint64_t* s_mma = s_full + 1;                                                    // its MMAs complete
+  uint64_t* s_tfree = s_mma + 1;                                                   // [2] accumulator read out
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_tfree + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+  const int n_steps = p.tc->steps, n_pad = p.tc->n_pad;
+  for (int i = tid; i < 32 * G; i += blockDim.x) s_tw[i] = p.tw2d[i];
+  {  // positions nobody publishes (the Nyquist chunk's tail, the padding chunk) stay zero; B blocks come prepared
+    uint4* a4 = reinterpret_cast<uint4*>(s_a);
+    for (int i = tid; i < Tc2::kOperand / 16; i += blockDim.x) a4[i] = make_uint4(0, 0, 0, 0);
+    const uint4* src = reinterpret_cast<const uint4*>(p.tc_b);
+    uint4* b4 = reinterpret_cast<uint4*>(s_b);
+    const int n16 = p.tc->b_bytes / 16;
+    for (int i = tid; i < n16; i += blockDim.x) b4[i] = src[i];
+  }
+  if (tid < n_steps) {
+    const TcStep st = p.tc->step[tid];
+    TcIssue2 o;
+    // A: 64 rows = 8 row groups 128 B apart (hi / lo of four 8-frame groups), the two K chunks kStride apart
+    o.a = umma_smem_desc(smem_u32(s_a) + st.kstep * 2 * kStride, kStride, 128);
+    o.b = umma_smem_desc(smem_u32(s_b) + st.b_off, st.n * 32, 128);  // 2 n rows: per 8 filters, 8 hi rows then 8 lo rows
+    o.idesc = umma_idesc_bf16(64, 2 * (int)st.n);
+    o.col = 2 * st.col;
+    o.pad0 = o.pad1 = 0;
+    s_issue[tid] = o;
+  }
+  if (tid < NW) mbar_init(s_bar + tid, 1);
+  if (tid == 0) {
+    mbar_init(s_full, NW);
+    mbar_init(s_mma, 1);
+    mbar_init(s_tfree + 0, kQuads);
+    mbar_init(s_tfree + 1, kQuads);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // B blocks, zeroed buffer -> the tensor core
+  __syncthreads();
+
+  const int64_t stride = (int64_t)gridDim.x * NW;
+  const int64_t u0 = (int64_t)blockIdx.x * NW;
+  const int width = p.out_width;
+
+  if (warp < NW) {
+    // =============================== transform warps ===========================================
+    reg_alloc<Tc2::kFftRegs>();
+    float2* tile = s_tile_all + warp * Ge::kTileF2;
+    float* stage = reinterpret_cast<float*>(tile);
+    uint64_t* bar = s_bar + warp;
+    float wreg[32];
+    load_window<G>(p, lane, wreg);
+    const int half = frame_lead(p, Ge::kNfft);
+    const int l = lane;
+    uint32_t parity = 0;
+    bool staged = false;
+    UnitCursor cur;
+    cur.init(u0 + warp, stride, p.units_per_row);
+    if (bulk_eligible<G>(p, half, cur.u, cur.ub)) {
+      if (lane == 0) issue_bulk<G>(p, half, cur.row, cur.ub, stage, bar);
+      staged = true;
+    }
+    // frames 2 warp (a) and 2 warp + 1 (b) are rows (r & 7) of frame group r >> 3; K position 64 j + 2 l (+1):
+    // chunk 8 j + (l >> 2), byte (l & 3) * 4 of the 16-byte row.  32 lanes -> 8 chunks x 4 words: conflict free.
+    const int row_a = 2 * warp;
+    unsigned char* dst = s_a + (l >> 2) * kStride + (row_a >> 3) * 256 + (row_a & 7) * 16 + (l & 3) * 4;
+    stagger_start(warp, p.skew_cycles);
+    int it = 0;
+    for (int64_t base = u0; base < p.total_units; base += stride, ++it, cur.advance()) {
+      const bool valid = cur.u < p.total_units;
+      float pa[17], pb[17];
+      if (valid)
+        transform_unit<POWER_MODE, G, HG, true, KALDI>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
+                                                       pb);
+      if (it >= 1) mbar_wait(s_mma, (uint32_t)(it & 1) ^ 1u);  // the tensor core has consumed the previous tile
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t ha, la, hb, lb;
+          split_bf16x2(pa[2 * j], pa[2 * j + 1], ha, la);
+          split_bf16x2(pb[2 * j], pb[2 * j + 1], hb, lb);
+          unsigned char* d = dst + j * (8 * kStride);
+          *reinterpret_cast<uint32_t*>(d) = ha;
+          *reinterpret_cast<uint32_t*>(d + 16) = hb;
+          *reinterpret_cast<uint32_t*>(d + 128) = la;
+          *reinterpret_cast<uint32_t*>(d + 144) = lb;
+        }
+        if (l == 0) {  // bin n_fft / 2 opens chunk 64; its partner position is padding
+          uint32_t ha, la, hb, lb;
+          split_bf16x2(pa[16], 0.f, ha, la);
+          split_bf16x2(pb[16], 0.f, hb, lb);
+          unsigned char* d = dst + 8 * (8 * kStride);
+          *reinterpret_cast<uint32_t*>(d) = ha;
+          *reinterpret_cast<uint32_t*>(d + 16) = hb;
+          *reinterpret_cast<uint32_t*>(d + 128) = la;
+          *reinterpret_cast<uint32_t*>(d + 144) = lb;
+        }
+      }
+      if (l == 0) {
+        const int64_t ta = cur.ub * Ge::kFrames;
+        const int64_t oa = (cur.row * p.frames + ta) * (int64_t)width + p.out_col0;
+        s_slot[row_a] = (valid && ta < p.frames) ? oa : -1;
+        s_slot[row_a + 1] = (valid && ta + 1 < p.frames) ? oa + width : -1;
+        const int64_t g = cur.row / p.rows_per_group;
+        s_grp[row_a] = g;
+        s_grp[row_a + 1] = g;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my operand words -> the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_full);
+    }
+  } else {
+    // ============ service warps: epilogue (the first kQuads of them), MMA issue (the last) ============
+    reg_dealloc<Tc2::kSvcRegs>();  // one setmaxnreg for the whole warpgroup
+    const int cw = warp - NW;      // == TMEM lane quadrant (NW % 4 == 0)
+    static_assert(NW % 4 == 0, "service warp i must own TMEM lane quadrant i");
+    const uint32_t acc_cols = 2 * n_pad;  // one accumulator; two of them alternate
+    const uint32_t tmem_cols =
+        acc_cols <= 16 ? 32u : (acc_cols <= 32 ? 64u : (acc_cols <= 64 ? 128u : (acc_cols <= 128 ? 256u : 512u)));
+    if (cw == 0) tmem_alloc(s_tmem, tmem_cols);
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"n"(kMelWarps * 32) : "memory");
+    tc_fence_after();
+    const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+    GroupMax gmax{p.stage == B200A_STAGE_FEAT ? p.group_max : nullptr, -1, -CUDART_INF_F};
+    // epilogue thread i < 8 owns frame 8 cw + i: its hi-plane row is TMEM lane 32 cw + i, its lo-plane row lane + 8
+    const int erow = 8 * cw + (lane & 7);
+
+    auto epilogue = [&](int t, int64_t o, int64_t g) {
+      const uint32_t acc = tmem_d + ((uint32_t)(32 * cw) << 16) + (uint32_t)(t & 1) * acc_cols;
+      const bool row_ok = lane < 8 && o >= 0;
+#pragma unroll 1
+      for (int f0 = 0; f0 < n_pad; f0 += 16) {
+        float u[16], w[16], v[16];
+        tmem_ld16(acc + 2 * f0, u);
+        tmem_ld16(acc + 2 * f0 + 16, w);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[q] = u[q] + u[q + 8];          // x F_hi + x F_lo
+          v[q + 8] = w[q] + w[q + 8];
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], 8);  // P_hi row + P_lo row
+        if (p.k_log) {  // Kaldi fbank: log(max(mel, FLT_EPSILON)), kaldi.py:629-631
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0.69314718055994531f * __log2f(fmaxf(v[q], kKaldiEps));
+        }
+        if (p.stage == B200A_STAGE_FEAT) {
+          float mx = -CUDART_INF_F;
+          const float scale = p.log_mels ? 0.69314718055994531f : p.db_mult * 0.30102999566398120f;
+          const float offs = p.log_mels ? 0.f : p.db_offset;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float arg = p.log_mels ? v[q] + 1e-6f : fmaxf(v[q], p.db_amin);
+            v[q] = fmaf(scale, __log2f(arg), -offs);
+            if (f0 + q < p.n_mels) mx = fmaxf(mx, v[q]);
+          }
+          gmax.add(g, mx, row_ok);
+        }
+        if (row_ok) {
+          float* dsto = p.out + o + f0;
+          if (p.out_vec >= 4 && f0 + 16 <= p.n_mels) {
+#pragma unroll
+            for (int q = 0; q < 16; q += 4)
+              *reinterpret_cast<float4*>(dsto + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (f0 + q < p.n_mels) dsto[q] = v[q];
+          }
+        }
+      }
+      tc_fence_before();  // my tcgen05.ld are done before this accumulator is handed back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_tfree + (t & 1));
+    };
+
+    int it = 0;
+    int64_t o_prev = -1, g_prev = -1;
+    for (int64_t base = u0; base < p.total_units; base += stride, ++it) {
+      mbar_wait(s_full, (uint32_t)it & 1u);
+      if (cw == kMelWarps - 1) {
+        // ---- issue: D[it & 1][:, 2 n0 : 2 n0 + 2 N] += [P_hi ; P_lo] [F_hi | F_lo], ONE instruction per k-step ----
+        if (it >= 2) mbar_wait(s_tfree + (it & 1), ((uint32_t)(it >> 1) & 1u) ^ 1u);  // tile it - 2 has left this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_d + (uint32_t)(it & 1) * acc_cols;
+#pragma unroll 3
+        for (int s = 0; s < n_steps; ++s) {
+          const TcIssue2 e = s_issue[s];
+          if (elect_one()) umma_bf16(acc + e.col, e.a, e.b, e.idesc, s > 0 ? 1u : 0u);  // step 0 spans every column
+        }
+        if (elect_one()) umma_commit(s_mma);
+        __syncwarp();
+      } else if (cw < kQuads) {
+        // the slots of tile `it` must be read before its MMAs complete (then the transform warps overwrite them)
+        int64_t o_cur = -1, g_cur = -1;
+        if (erow < kRows) {
+          o_cur = s_slot[erow];
+          g_cur = s_grp[erow];
+        }
+        if (it > 0) {  // tile it could only be published after the MMAs of tile it - 1 completed (single operand buffer)
+          tc_fence_after();
+          epilogue(it - 1, o_prev, g_prev);
+        }
+        o_prev = o_cur;
+        g_prev = g_cur;
+      }
+    }
+    if (cw < kQuads && cw != kMelWarps - 1 && it > 0) {
+      mbar_wait(s_mma, (uint32_t)(it - 1) & 1u);
+      tc_fence_after();
+      epilogue(it - 1, o_prev, g_prev);
+    }
+    gmax.flush();
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"n"(kMelWarps * 32) : "memory");  // every tcgen05.ld is done
+    if (cw == 0) tmem_dealloc(tmem_d, tmem_cols);
+  }
+}
+
+int tc_b_budget(int n_fft) {
+  return n_fft == 1024 ? Tc2::kBBudget : (n_fft == 512 ? TcGeo<16>::kBBudget : TcGeo<8>::kBBudget);
+}
+
 // The mel / MFCC-feature kernel: tcgen05 contraction when the prepared plan says the banded filterbank fits
 // shared memory (every real mel / linear filterbank does), mma.sync contraction otherwise.
 template <int POWER_MODE, int G, int HG, bool KALDI>
@@ -1540,10 +1843,12 @@ __global__ void __launch_bounds__(TcGeo<G>::kThreads, 1) stft_pow2_mel_kernel(co
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // 512 threads start with 128 registers each: 8 x 32 x 192 + 4 x 32 x 96 + 4 x 32 x 24 <= 65536
   constexpr int kMmaFftRegs = TcGeo<G>::kThreads == 512 ? 192 : kFftRegs;
-  if (p.tc != nullptr && p.tc->ok)
-    mel_body_tc<POWER_MODE, G, HG, KALDI>(p, smem_raw);
-  else
+  if (p.tc != nullptr && p.tc->ok) {
+    if constexpr (G == 32) mel_body_tc2<POWER_MODE, HG, KALDI>(p, smem_raw);
+    else mel_body_tc<POWER_MODE, G, HG, KALDI>(p, smem_raw);
+  } else {
     mel_body_mma<POWER_MODE, G, HG, kMmaFftRegs, KALDI>(p, smem_raw);
+  }
 }
 
 // ================================================================================================
@@ -1738,8 +2043,8 @@ int pow2_prepare(const b200a_frontend_desc* d, void* ws, size_t ws_bytes, cudaSt
   }
   if (tc_enabled(*d)) {
     prepare_tc_kernel<<<1, 256, 0, stream>>>(reinterpret_cast<const float*>(base + l.fb), d->n_fft / 2 + 1, d->n_mels,
-                                             d->n_fft, tc_b_budget(d->n_fft), reinterpret_cast<TcPlan*>(base + e.tc_plan),
-                                             base + e.tc_b);
+                                             d->n_fft, tc_b_budget(d->n_fft), d->n_fft == 1024 ? 32 : 0,
+                                             reinterpret_cast<TcPlan*>(base + e.tc_plan), base + e.tc_b);
   }
   return launch_status();
 }
@@ -1922,6 +2227,14 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
   p.out_vec = (p.out_width % 4 == 0 && p.out_col0 % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)   ? 4
               : (p.out_width % 2 == 0 && p.out_col0 % 2 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) ? 2
                                                                                                               : 1;
+  {
+    // B200A_SKEW=<cycles>: start-up stagger of the transform warps (0 disables); default tuned on B200
+    static const int skew = [] {
+      const char* e = std::getenv("B200A_SKEW");
+      return e ? std::atoi(e) : kDefaultSkewCycles;
+    }();
+    p.skew_cycles = skew;
+  }
   const bool mel = stage >= B200A_STAGE_MEL;
   if (eo) {
     p.bulk_ok = d->hop % 4 == 0 && (half + d->pad) % 4 == 0 && row_stride % 4 == 0 &&

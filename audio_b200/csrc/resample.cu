@@ -45,22 +45,23 @@ constexpr int kRsMaxTiles = 128;     // groups of 8 phases  (new' <= 1024)
 constexpr int kRsSmemBudget = 224 * 1024;
 
 struct RsTile {  // one group of 8 phases
-  int kstart;    // first tap of its first k-step (multiple of 8)
-  int nsteps;    // 8-tap k-steps covering the union of the group's live taps
-  int frag_off;  // first step in the fragment array
-  int pad;
+  int kstart;      // first tap of its first k-step (multiple of 8)
+  int nsteps;      // 8-tap k-steps covering the union of the group's live taps
+  int frag_off;    // first step in the TF32 fragment array
+  int frag16_off;  // first 16-tap step in the bf16 fragment array
 };
 
 struct RsHeader {
   uint32_t magic;
   int32_t orig_r, new_r, width, taps, max_support, n_tiles, total_steps;
   int32_t simt_tap_floats;  // size of the SIMT tap table (floats)
-  int32_t reserved[7];
+  int32_t total_steps16;    // 16-tap steps over all groups (bf16 fragments)
+  int32_t reserved[6];
 };
 static_assert(sizeof(RsHeader) == 64, "header is 64 bytes");
 
 struct RsLayout {
-  size_t header, support, tiles, frags, sgroups, staps, total;
+  size_t header, support, tiles, frags, frags16, sgroups, staps, total;
 };
 
 struct RsSimtGroup {  // one group of 8 phases for the SIMT kernel
@@ -84,6 +85,8 @@ inline RsLayout rs_layout(int new_r, int taps) {
   l.frags = off;  // worst case: every group spans every tap
   const size_t nt = rs_tiles(new_r) <= kRsMaxTiles ? rs_tiles(new_r) : 0;
   off = align_up(off + sizeof(float4) * 32 * nt * ((size_t)taps / 8 + 2), 256);
+  l.frags16 = off;  // bf16 hi / lo fragments of the 16-tap steps (resample_mma_kernel<true>)
+  off = align_up(off + sizeof(uint4) * 32 * nt * ((size_t)taps / 16 + 2), 256);
   l.sgroups = off;
   off = align_up(off + sizeof(RsSimtGroup) * (size_t)rs_tiles(new_r), 256);
   l.staps = off;  // worst case: every group spans every tap
@@ -130,26 +133,35 @@ __global__ void resample_support_kernel(const float* __restrict__ kernel, int ne
 
 // Per group of 8 phases: the k-steps its live taps span, and the taps split into TF32 hi/lo parts in
 // mma.m16n8k8 B-fragment order (B[k][n] = K[8 t + n][kstart + k]).
+// (x, y) -> packed bf16 pair (x in the low half) and the packed pair of the residuals
+__device__ __forceinline__ void rs_split_bf16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));
+  const float rx = x - __uint_as_float(hi << 16), ry = y - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(ry), "f"(rx));
+}
+
 __global__ void resample_plan_kernel(const float* __restrict__ kernel, const int2* __restrict__ support, int new_r,
-                                     int taps, int n_tiles, RsHeader* hdr, RsTile* tiles, float4* frags) {
+                                     int taps, int n_tiles, RsHeader* hdr, RsTile* tiles, float4* frags, uint4* frags16) {
   if (threadIdx.x == 0) {
-    int acc = 0;
+    int acc = 0, acc16 = 0;
     for (int t = 0; t < n_tiles; ++t) {
       int lo = taps, hi = 0;
       for (int j = 8 * t; j < min(8 * t + 8, new_r); ++j) {
         const int2 sp = support[j];
         if (sp.y > 0) { lo = min(lo, sp.x); hi = max(hi, sp.x + sp.y); }
       }
-      RsTile rt{0, 0, acc, 0};
+      RsTile rt{0, 0, acc, acc16};
       if (hi > lo) {
         rt.kstart = lo & ~7;
         rt.nsteps = (hi - rt.kstart + 7) / 8;
       }
       tiles[t] = rt;
       acc += rt.nsteps;
+      acc16 += (rt.nsteps + 1) / 2;
     }
     hdr->n_tiles = n_tiles;
     hdr->total_steps = acc;
+    hdr->total_steps16 = acc16;
   }
   __syncthreads();
   for (int t = 0; t < n_tiles; ++t) {
@@ -164,6 +176,24 @@ __global__ void resample_plan_kernel(const float* __restrict__ kernel, const int
       const float b1h = __uint_as_float(__float_as_uint(b1) & 0xffffe000u);
       frags[(size_t)(rt.frag_off + s) * 32 + lane] = make_float4(b0h, b1h, b0 - b0h, b1 - b1h);
     }
+    // 16-tap steps for mma.m16n8k16 bf16: the instruction's k index is a PERMUTATION of the taps chosen so that a
+    // thread's A elements (k = 2c, 2c+1, 2c+8, 2c+9) are taps c, c+4, c+8, c+12 of the step -- the same
+    // conflict-free shared-memory reads as the 8-tap TF32 steps.  B[k][n] follows the same permutation.
+    const int n16 = (rt.nsteps + 1) / 2;
+    for (int i = threadIdx.x; i < n16 * 32; i += blockDim.x) {
+      const int s = i >> 5, lane = i & 31;
+      const int j = 8 * t + (lane >> 2), c = lane & 3;
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = rt.kstart + 16 * s + c + 4 * q;
+        v[q] = (j < new_r && k < taps && k < rt.kstart + 8 * rt.nsteps) ? kernel[(size_t)j * taps + k] : 0.f;
+      }
+      uint4 f;
+      rs_split_bf16x2(v[0], v[1], f.x, f.z);  // b0: taps c, c + 4
+      rs_split_bf16x2(v[2], v[3], f.y, f.w);  // b1: taps c + 8, c + 12
+      frags16[(size_t)(rt.frag16_off + s) * 32 + lane] = f;
+    }
   }
 }
 
@@ -175,6 +205,7 @@ struct RsParams {
   const RsHeader* hdr;
   const RsTile* tiles;
   const float4* frags;
+  const uint4* frags16;
   int orig_r, new_r, width, taps, n_tiles;
   int64_t frames;           // output frames per row = ceil(out_len / new_r)
   int64_t blocks_per_row;   // ceil(frames / kRsFrames)
@@ -195,7 +226,7 @@ __device__ __forceinline__ int rs_fill(const RsParams& p, int64_t row, int64_t f
   // addresses, so the tile is shifted by 0..3 floats until the two alignments agree
   const int a0 = (int)((reinterpret_cast<uintptr_t>(x) >> 2) & 3);
   const int shift = (int)((((a0 + T0) % 4) + 4) % 4);  // xs index of sample g: q = g - T0 + shift == a0 + g (mod 4)
-  const int64_t span = (int64_t)kRsFrames * p.orig_r + p.taps + 8;
+  const int64_t span = (int64_t)kRsFrames * p.orig_r + p.taps + 16;  // + the zero-tap tail of the last 16-tap step
   const int64_t lo = T0 < 0 ? 0 : T0;
   int64_t hi = T0 + span;
   if (hi > p.length) hi = p.length;
@@ -237,6 +268,16 @@ __device__ __forceinline__ int frame_of(int spread, int h, int rho) {
   return 16 * h + rho;
 }
 
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// BF16 == false: m16n8k8 TF32 x 3 (2^-21 relative);  BF16 == true: m16n8k16 bf16 x 3 (2^-16 relative, half the
+// tensor-pipe time: the TF32 variant is throttled by the math pipe, profiles/r1_resample_v4.txt)
+template <bool BF16>
 __global__ void __launch_bounds__(kRsMaxWarps * 32, 1) resample_mma_kernel(const RsParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_x = reinterpret_cast<float*>(smem_raw);                              // [2][xs_floats]
@@ -246,10 +287,12 @@ __global__ void __launch_bounds__(kRsMaxWarps * 32, 1) resample_mma_kernel(const
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < p.n_tiles; i += blockDim.x) s_tiles[i] = p.tiles[i];
-  const int total_steps = p.hdr->total_steps;
+  const int total_steps = BF16 ? p.hdr->total_steps16 : p.hdr->total_steps;
   const bool frags_in_smem = (size_t)total_steps * 512 <= (size_t)p.frag_smem_bytes;
-  if (frags_in_smem)
-    for (int i = tid; i < total_steps * 32; i += blockDim.x) s_frags[i] = p.frags[i];
+  if (frags_in_smem) {
+    const float4* src = BF16 ? reinterpret_cast<const float4*>(p.frags16) : p.frags;
+    for (int i = tid; i < total_steps * 32; i += blockDim.x) s_frags[i] = src[i];
+  }
   if (tid == 0) {
     mbar_init(s_bar + 0, 1);
     mbar_init(s_bar + 1, 1);
@@ -304,6 +347,31 @@ __global__ void __launch_bounds__(kRsMaxWarps * 32, 1) resample_mma_kernel(const
 #pragma unroll
           for (int q = 0; q < 4; ++q) d[h][ch][q] = 0.f;
       auto contract = [&](auto in_smem) {
+        if constexpr (BF16) {
+          const uint4* frg = (decltype(in_smem)::value ? reinterpret_cast<const uint4*>(s_frags) : p.frags16) +
+                             (size_t)rt.frag16_off * 32 + lane;
+          const int n16 = (rt.nsteps + 1) >> 1;
+#pragma unroll 2
+          for (int s = 0; s < n16; ++s) {
+            uint4 bf;
+            if constexpr (decltype(in_smem)::value) bf = frg[(size_t)s * 32];
+            else bf = __ldg(frg + (size_t)s * 32);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              // k = 2c, 2c+1 <-> taps c, c+4;  k = 2c+8, 2c+9 <-> taps c+8, c+12 (see resample_plan_kernel)
+              const float* lo_row = arow[2 * h] + 16 * s;
+              const float* hi_row = arow[2 * h + 1] + 16 * s;
+              uint32_t ah[4], al[4];
+              rs_split_bf16x2(lo_row[0], lo_row[4], ah[0], al[0]);
+              rs_split_bf16x2(hi_row[0], hi_row[4], ah[1], al[1]);
+              rs_split_bf16x2(lo_row[8], lo_row[12], ah[2], al[2]);
+              rs_split_bf16x2(hi_row[8], hi_row[12], ah[3], al[3]);
+              mma_bf16_16816(d[h][0], ah, bf.x, bf.y);
+              mma_bf16_16816(d[h][1], al, bf.x, bf.y);
+              mma_bf16_16816(d[h][2], ah, bf.z, bf.w);
+            }
+          }
+        } else {
         const float4* frg = (decltype(in_smem)::value ? s_frags : p.frags) + (size_t)rt.frag_off * 32 + lane;
 #pragma unroll 2
         for (int s = 0; s < rt.nsteps; ++s) {
@@ -321,6 +389,7 @@ __global__ void __launch_bounds__(kRsMaxWarps * 32, 1) resample_mma_kernel(const
             mma_tf32(d[h][1], lo, __float_as_uint(bf.x), __float_as_uint(bf.y));
             mma_tf32(d[h][2], hi, __float_as_uint(bf.z), __float_as_uint(bf.w));
           }
+        }
         }
       };
       if (frags_in_smem) contract(std::true_type{});
@@ -625,7 +694,8 @@ int resample_prepare_impl(const float* kernel, int orig_r, int new_r, int width,
   if (rs_tiles(new_r) <= kRsMaxTiles)
     resample_plan_kernel<<<1, 256, 0, stream>>>(kernel, support, new_r, taps, rs_tiles(new_r), hdr,
                                                 reinterpret_cast<RsTile*>(base + l.tiles),
-                                                reinterpret_cast<float4*>(base + l.frags));
+                                                reinterpret_cast<float4*>(base + l.frags),
+                                                reinterpret_cast<uint4*>(base + l.frags16));
   resample_simt_plan_kernel<<<1, 256, 0, stream>>>(kernel, support, new_r, taps, rs_tiles(new_r), hdr,
                                                    reinterpret_cast<RsSimtGroup*>(base + l.sgroups),
                                                    reinterpret_cast<float*>(base + l.staps));
@@ -658,7 +728,7 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
     const int slot_floats = (32 * orig_r + 2 * width + 3 + 8 + 3) & ~3;  // span + alignment shift + zero-tap over-read
     const size_t ring_bytes = sizeof(float) * 3 * (size_t)slot_floats;
     const size_t fixed = ring_bytes + sizeof(RsSimtGroup) * (size_t)n_groups + 64;
-    const bool want = forced == 1 || (forced == 0 && (orig_r & 1) == 1 && n_groups >= 4);
+    const bool want = forced == 1;  // measured slower than the tensor-pipe kernel (0.446 vs 0.391 ms at config 3): opt-in only
     if (want && fixed + 8192 <= (size_t)227 * 1024 && (reinterpret_cast<uintptr_t>(wave) & 3) == 0 &&
         length + (int64_t)taps + 64 * (int64_t)orig_r < ((int64_t)1 << 31)) {
       RsSimtParams p{};
@@ -702,7 +772,7 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
 
   // ---- tensor-pipe path -------------------------------------------------------------------------
   const int n_tiles = rs_tiles(new_r);
-  const int xs_floats = (kRsFrames * orig_r + taps + 8 + 4 + 3) & ~3;
+  const int xs_floats = (kRsFrames * orig_r + taps + 16 + 4 + 3) & ~3;
   const size_t smem_fixed = sizeof(float) * 2 * (size_t)xs_floats + 16 + sizeof(RsTile) * ((n_tiles + 3) & ~3);
   const bool aligned = (reinterpret_cast<uintptr_t>(wave) & 3) == 0;  // any float pointer; rows may have any pitch
   if (forced != 3 && n_tiles <= kRsMaxTiles && aligned && smem_fixed + 1024 <= (size_t)kRsSmemBudget) {
@@ -717,6 +787,7 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
     p.hdr = reinterpret_cast<const RsHeader*>(base + l.header);
     p.tiles = reinterpret_cast<const RsTile*>(base + l.tiles);
     p.frags = reinterpret_cast<const float4*>(base + l.frags);
+    p.frags16 = reinterpret_cast<const uint4*>(base + l.frags16);
     p.orig_r = orig_r;
     p.new_r = new_r;
     p.width = width;
@@ -730,8 +801,9 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
     // device-side step count with the room granted here), otherwise they are read through L1
     p.frag_smem_bytes = (int)(((size_t)kRsSmemBudget - smem_fixed) & ~(size_t)511);  // everything that is left
     const size_t smem = smem_fixed + p.frag_smem_bytes;
-    if (cudaFuncSetAttribute(resample_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-        cudaSuccess)
+    // B200A_RS=mma keeps the TF32 x 3 arithmetic; the default is the bf16 x 3 variant (half the tensor-pipe time)
+    auto kern = forced == 2 ? resample_mma_kernel<false> : resample_mma_kernel<true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return B200A_ECUDA;
     int64_t grid = p.total_blocks < sms ? p.total_blocks : sms;
     if (grid < 1) grid = 1;
@@ -758,7 +830,7 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
       const double idle = 1.0 - (double)items / (double)(rounds * w);
       if (idle <= best_idle + 1e-9) { best_idle = idle; warps = w; }  // ties go to more warps
     }
-    resample_mma_kernel<<<(unsigned)grid, warps * 32, smem, stream>>>(p);
+    kern<<<(unsigned)grid, warps * 32, smem, stream>>>(p);
     return launch_status();
   }
 

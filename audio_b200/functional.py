@@ -115,7 +115,8 @@ def _check_window_envelope(window: Tensor, n_fft: int, win_length: int, hop: int
     ("window overlap add min"); it finds out with a device synchronisation, and so does this check -- once per
     (window tensor, geometry).  The cache entry HOLDS the window tensor, so its (data_ptr, _version) key cannot
     be matched by a different window that was handed the recycled allocation; the cache is a bounded LRU."""
-    key = (window.data_ptr(), window._version, str(window.device), n_fft, win_length, hop, frames, start, end)
+    key = (window.data_ptr(), -1 if window.is_inference() else window._version, str(window.device), n_fft, win_length,
+           hop, frames, start, end)
     if key in _ENVELOPE_OK:
         _ENVELOPE_OK.move_to_end(key)
         return

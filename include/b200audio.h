@@ -99,6 +99,11 @@ int32_t b200a_num_bins(int32_t n_fft, int32_t onesided);
 int32_t b200a_resample_width(int32_t orig_r, int32_t new_r, int32_t lowpass_filter_width, double rolloff);
 /* ceil(new'*L/orig') evaluated as the reference does (functional.py:1427). */
 int64_t b200a_resample_len(int64_t length, int32_t orig_r, int32_t new_r);
+/* Live taps [first, first + count) of output phase `phase` of the (new', 2*width+orig') sinc kernel: the taps whose
+ * window argument lies strictly inside +-lowpass_filter_width (functional.py:1376-1400); every other tap of the row
+ * is (numerically) zero.  ~2*lpw*orig'/min(orig',new') taps.  Returns 0 or B200A_EINVAL. */
+int b200a_resample_support(int32_t orig_r, int32_t new_r, int32_t lowpass_filter_width, double rolloff, int32_t phase,
+                           int32_t* first, int32_t* count);
 
 /* ---- fused front end -------------------------------------------------------------------- */
 /* Bytes of caller-owned device workspace that b200a_frontend_prepare fills for this descriptor. */
