@@ -48,7 +48,6 @@ namespace b200a {
 
 namespace {
 
-constexpr int kDefaultSkewCycles = 0;  // start-up stagger between warps of one scheduler (B200A_SKEW overrides)
 constexpr float kKaldiEps = 1.1920928955078125e-07f;  // numeric_limits<float>::epsilon(), kaldi.py:21-22
 constexpr int kPadSymmetric = 4;  // internal pad mode: x[-1-j] = x[j], x[L+j] = x[L-1-j] (Kaldi snip_edges = false)
 constexpr int kWarps = 8;     // transform warps per CTA
@@ -184,11 +183,12 @@ __device__ __forceinline__ void bfly(float2& a, float2& b) {
 
 // In-register LEN-point DFT on a[OFF .. OFF+LEN).  Input a[OFF + brev<log2 LEN>(j)] = x[j]; output
 // a[OFF + k] = X[k] (natural order).
-template <int LEN, int OFF>
+template <int LEN, int OFF, int S0 = 0, int S1 = 5>
 __device__ __forceinline__ void fft_regs(float2 (&a)[32]) {
   constexpr int kStages = LEN == 32 ? 5 : (LEN == 16 ? 4 : 3);
-  static_for<kStages>([&](auto si) {
-    constexpr int len = 2 << decltype(si)::value;  // 2, 4, ..., LEN
+  constexpr int kFirst = S0, kLast = S1 < kStages ? S1 : kStages;  // stages [kFirst, kLast)
+  static_for<kLast - kFirst>([&](auto si) {
+    constexpr int len = 2 << (decltype(si)::value + kFirst);  // 2, 4, ..., LEN
     constexpr int half = len / 2;
     static_for<LEN / 2>([&](auto bi) {
       constexpr int b = decltype(bi)::value;
@@ -213,7 +213,6 @@ struct Pow2Params {
   const unsigned char* tc_b;   // its banded bf16 B blocks
   int hop, pad, center, pad_mode, n_mels;
   int stage, log_mels, bulk_ok, stage_ok;
-  int skew_cycles;  // start-up stagger between the transform warps of one scheduler (see stagger_start)
   // output row geometry: value m of frame t goes to out[(row * frames + t) * out_width + out_col0 + m]
   int out_width, out_col0, out_vec;  // out_vec: floats every row start is aligned to (1, 2 or 4)
   // Kaldi framing / per-frame conditioning (compliance/kaldi.py:44-83, :153-216); kaldi == 0: torch.stft framing
@@ -274,19 +273,6 @@ __device__ __forceinline__ void reg_alloc() {
 template <int N>
 __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
-}
-
-// The transform warps of a CTA run the same long sequence of phases (shared-memory loads, FP-dense register FFT,
-// transpose, FFT, shuffles, stores).  Started together they stay roughly in phase, so the warps sharing a scheduler all
-// want the FMA pipe at once and then all want the load/store pipe at once ("math pipe throttle" next to an FMA
-// pipe that is idle half of the time, profiles/r2_mel_v2.txt).  A one-time stagger at start-up -- warp w of
-// scheduler w % 4 waits (w / 4) * skew cycles -- puts them in different phases for the rest of the kernel.
-__device__ __forceinline__ void stagger_start(int warp, int skew_cycles) {
-  const long long wait = (long long)(warp >> 2) * skew_cycles;
-  if (wait > 0) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < wait) __nanosleep(64);
-  }
 }
 
 // Per-warp walker over this warp's units: (row, unit-in-row) of the current and the next unit,
@@ -510,15 +496,24 @@ __device__ __forceinline__ void transform_unit(const Pow2Params& p, const float 
     if (staged && lane == 0) issue_bulk<G>(p, half, cur.nrow, cur.nub, stage, bar);
   }
 
-  fft_regs<32, 0>(a);  // a[k2] = Y[l][k2]
-
-  // twiddle + transpose inside the lane group: element (l, k2) -> region[k2][l]
+  // the inter-pass twiddles: kTwAhead loads are in flight before the last butterfly stage, and every multiply
+  // issues the load kTwAhead positions ahead of it, so no multiply waits for its own load
+#ifndef B200A_TW_AHEAD
+#define B200A_TW_AHEAD 8
+#endif
+  constexpr int kTwAhead = B200A_TW_AHEAD;
+  fft_regs<32, 0, 0, 4>(a);
+  float2 tw[32];
+  static_for<kTwAhead>([&](auto ki) {
+    constexpr int k2 = decltype(ki)::value + 1;
+    tw[k2] = s_tw[k2 * G + l];
+  });
+  fft_regs<32, 0, 4, 5>(a);  // a[k2] = Y[l][k2]
   grp_tile[l] = a[0];
   static_for<31>([&](auto ki) {
     constexpr int k2 = decltype(ki)::value + 1;
-    const float2 w = s_tw[k2 * G + l];
-    const float2 v = a[k2];
-    grp_tile[k2 * Ge::kRowLd + l] = cmul2(v, w);
+    if constexpr (k2 + kTwAhead < 32) tw[k2 + kTwAhead] = s_tw[(k2 + kTwAhead) * G + l];
+    grp_tile[k2 * Ge::kRowLd + l] = cmul2(a[k2], tw[k2]);
   });
   __syncwarp();
   // lane l now owns k2 = l + G q, q < 32/G: slot q*G + brev(g) <- element (g, l + G q)
@@ -627,7 +622,6 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_pow2_power_kernel(const Pow2P
     if (lane == 0) issue_bulk<G>(p, half, cur.row, cur.ub, stage, bar);
     staged = true;
   }
-  stagger_start(warp, p.skew_cycles);
   for (; cur.u < p.total_units; cur.advance()) {
     float pa[17], pb[17];
     transform_unit<POWER_MODE, G, HG, STAGE_IS_TILE, KALDI>(p, wreg, s_tw, tile, stage, bar, parity, staged, cur, half, lane, pa,
@@ -1302,7 +1296,6 @@ __device__ __forceinline__ void mel_body_tc(const Pow2Params& p, unsigned char* 
     const int row_a = Ge::kFrames * warp + 2 * gi;  // even: rows a and a + 1 share the 8-row group
     const int lane_off = (l >> 3) * kStride + (row_a >> 3) * 256 + (row_a & 7) * 32 + (l & 7) * 4;
     constexpr int kStepM = (G / 8) * kStride;
-    stagger_start(warp, p.skew_cycles);
     int it = 0;
     for (int64_t base = u0; base < p.total_units; base += stride, ++it, cur.advance()) {
       const bool valid = cur.u < p.total_units;
@@ -1678,7 +1671,6 @@ __device__ __forceinline__ void mel_body_tc2(const Pow2Params& p, unsigned char*
     // chunk 8 j + (l >> 2), byte (l & 3) * 4 of the 16-byte row.  32 lanes -> 8 chunks x 4 words: conflict free.
     const int row_a = 2 * warp;
     unsigned char* dst = s_a + (l >> 2) * kStride + (row_a >> 3) * 256 + (row_a & 7) * 16 + (l & 3) * 4;
-    stagger_start(warp, p.skew_cycles);
     int it = 0;
     for (int64_t base = u0; base < p.total_units; base += stride, ++it, cur.advance()) {
       const bool valid = cur.u < p.total_units;
@@ -2227,14 +2219,6 @@ int frontend_run_pow2(const b200a_frontend_desc* d, const void* ws, int stage, c
   p.out_vec = (p.out_width % 4 == 0 && p.out_col0 % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)   ? 4
               : (p.out_width % 2 == 0 && p.out_col0 % 2 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) ? 2
                                                                                                               : 1;
-  {
-    // B200A_SKEW=<cycles>: start-up stagger of the transform warps (0 disables); default tuned on B200
-    static const int skew = [] {
-      const char* e = std::getenv("B200A_SKEW");
-      return e ? std::atoi(e) : kDefaultSkewCycles;
-    }();
-    p.skew_cycles = skew;
-  }
   const bool mel = stage >= B200A_STAGE_MEL;
   if (eo) {
     p.bulk_ok = d->hop % 4 == 0 && (half + d->pad) % 4 == 0 && row_stride % 4 == 0 &&

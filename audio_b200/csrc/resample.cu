@@ -28,6 +28,7 @@
 // Half-chunks stream through a 3-slot ring of bulk asynchronous copies.  Step s pairs half-chunks (s-1, s) and
 // handles the phase groups of parity s & 1, so every half-chunk meets both parities (once as the newer, once as
 // the older member of a pair) and a slot is free for the next copy as soon as its second step ends.
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -56,13 +57,18 @@ struct RsHeader {
   int32_t orig_r, new_r, width, taps, max_support, n_tiles, total_steps;
   int32_t simt_tap_floats;  // size of the SIMT tap table (floats)
   int32_t total_steps16;    // 16-tap steps over all groups (bf16 fragments)
-  int32_t reserved[6];
+  int32_t r3_ok;            // 1: every group of 4 phases spans at most kR3Len taps (resample_r3_kernel applies)
+  int32_t reserved[5];
 };
 static_assert(sizeof(RsHeader) == 64, "header is 64 bytes");
 
 struct RsLayout {
-  size_t header, support, tiles, frags, frags16, sgroups, staps, total;
+  size_t header, support, tiles, frags, frags16, sgroups, staps, r3base, r3taps, total;
 };
+
+constexpr int kR3Len = 44;      // taps per phase quad held in registers (34 live + 3 x 2.76 drift at 441:160, padded)
+constexpr int kR3Warps = 10;    // warps per CTA == phase quads per CTA
+constexpr int kR3MaxCluster = 4;
 
 struct RsSimtGroup {  // one group of 8 phases for the SIMT kernel
   int base;  // first tap (xp-relative) any phase of the group uses
@@ -91,6 +97,11 @@ inline RsLayout rs_layout(int new_r, int taps) {
   off = align_up(off + sizeof(RsSimtGroup) * (size_t)rs_tiles(new_r), 256);
   l.staps = off;  // worst case: every group spans every tap
   off = align_up(off + sizeof(float) * 8 * (size_t)rs_tiles(new_r) * ((size_t)taps + 8), 256);
+  const size_t quads = ((size_t)new_r + 3) / 4;
+  l.r3base = off;
+  off = align_up(off + sizeof(int) * quads, 256);
+  l.r3taps = off;
+  off = align_up(off + sizeof(float4) * kR3Len * quads, 256);
   l.total = off;
   return l;
 }
@@ -213,6 +224,7 @@ struct RsParams {
   int xs_floats;            // floats per staging buffer
   int frag_smem_bytes;      // shared memory granted to the fragment copy (0: read them from global)
   int row_spread;           // 1, 2 or 4: frame distance of the 8 rows one A-fragment load touches
+  int skip_if_r3_ok;        // launched behind resample_r3_kernel: leave when the header says that kernel did the work
 };
 
 // Fill one staging buffer with the samples frames [f0, f0 + 32) of `row` need:
@@ -286,6 +298,7 @@ __global__ void __launch_bounds__(kRsMaxWarps * 32, 1) resample_mma_kernel(const
   float4* s_frags = reinterpret_cast<float4*>(s_tiles + ((p.n_tiles + 3) & ~3));  // optional
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (p.skip_if_r3_ok && p.hdr->r3_ok != 0) return;
   for (int i = tid; i < p.n_tiles; i += blockDim.x) s_tiles[i] = p.tiles[i];
   const int total_steps = BF16 ? p.hdr->total_steps16 : p.hdr->total_steps;
   const bool frags_in_smem = (size_t)total_steps * 512 <= (size_t)p.frag_smem_bytes;
@@ -401,9 +414,9 @@ __global__ void __launch_bounds__(kRsMaxWarps * 32, 1) resample_mma_kernel(const
       for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int half_row = 0; half_row < 2; ++half_row) {
-          const int64_t m = (f0 + fr[2 * h + half_row]) * p.new_r + j0;
           const float v0 = d[h][0][2 * half_row] + (d[h][1][2 * half_row] + d[h][2][2 * half_row]);
           const float v1 = d[h][0][2 * half_row + 1] + (d[h][1][2 * half_row + 1] + d[h][2][2 * half_row + 1]);
+          const int64_t m = (f0 + fr[2 * h + half_row]) * p.new_r + j0;
           if (pair_ok && m + 1 < p.out_len) {
             *reinterpret_cast<float2*>(orow + m) = make_float2(v0, v1);  // m even, row pitch even: 8-byte aligned
           } else {
@@ -651,6 +664,239 @@ __global__ void __launch_bounds__(kSimtMaxWarps * 32, 1) resample_simt_kernel(co
   }
 }
 
+// ---- cluster kernel tables: per QUAD of 4 phases the first live tap and kR3Len taps x 4 phases (zero padded) -------
+__global__ void resample_r3_plan_kernel(const float* __restrict__ kernel, const int2* __restrict__ support, int new_r,
+                                        int taps, int n_quads, RsHeader* hdr, int* qbase, float4* qtaps) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  for (int q = threadIdx.x; q < n_quads; q += blockDim.x) {
+    int lo = taps, hi = 0;
+    for (int j = 4 * q; j < min(4 * q + 4, new_r); ++j) {
+      const int2 sp = support[j];
+      if (sp.y > 0) { lo = min(lo, sp.x); hi = max(hi, sp.x + sp.y); }
+    }
+    if (hi <= lo) lo = hi = 0;
+    if (hi - lo > kR3Len) s_ok = 0;
+    qbase[q] = lo;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n_quads * kR3Len; e += blockDim.x) {
+    const int q = e / kR3Len, i = e - q * kR3Len, t = qbase[q] + i;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int j = 4 * q + r;
+      if (j < new_r && t < taps) {
+        const int2 sp = support[j];
+        if (t >= sp.x && t < sp.x + sp.y) v[r] = kernel[(size_t)j * taps + t];
+      }
+    }
+    qtaps[e] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  if (threadIdx.x == 0) hdr->r3_ok = s_ok;
+}
+
+// ================================================================================================
+// Cluster kernel (resample_r3_kernel): the taps never leave the register file.
+//   A register-tiled FIR is bound by shared-memory wavefronts unless BOTH operands of an FMA are reused from
+//   registers (docs/KERNEL_NOTES.md).  Here a warp owns ONE quad of 4 output phases for the whole kernel and keeps
+//   its 4 x kR3Len taps in 176 registers; lanes are the 32 frames of a tile, so the only shared-memory traffic is one
+//   conflict-free 4-byte read per tap position, feeding two FFMA2 (4 phases) with the sample as the broadcast operand.
+//   160 phases = 40 quads need 40 such warps; 204 registers per thread allow 10 per SM, so a CLUSTER of 4 CTAs covers
+//   the phases and shares every staged tile: each CTA fetches a quarter of the tile's samples with ONE bulk copy that is
+//   MULTICAST into the same offset of all four CTAs' shared memory (every HBM byte is read once), through a 3-slot ring
+//   with cluster-scope full / empty mbarriers.
+// ================================================================================================
+struct R3Params {
+  const float* wave;
+  int64_t rows, length, row_stride;
+  float* out;
+  int64_t out_row_stride, out_len;
+  const RsHeader* hdr;
+  const int* qbase;
+  const float4* qtaps;
+  int orig_r, new_r, width, n_quads, csize;
+  int64_t frames, tiles_per_row, total_tiles;
+  int slot_floats, out_vec;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// bulk copy global -> the same shared-memory offset of every CTA in `mask`, completing bytes on each one's mbarrier
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(2000u)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
+// Stage tile (row, f0) into ring slot `xs` of EVERY CTA of the cluster: local zero fill / unaligned head and tail by all
+// threads of each CTA, and this CTA's share of the 16-byte aligned body as one multicast bulk copy.  Returns `shift`.
+__device__ __forceinline__ void r3_fill(const R3Params& p, int64_t row, int64_t f0, float* xs, uint64_t* full, uint32_t crank,
+                                        int tid, int nthreads) {
+  const int64_t T0 = f0 * p.orig_r - p.width;
+  const float* x = p.wave + row * p.row_stride;
+  const int a0 = (int)((reinterpret_cast<uintptr_t>(x) >> 2) & 3);
+  const int shift = (int)((((a0 + T0) % 4) + 4) % 4);
+  const int64_t span = (int64_t)32 * p.orig_r + 2 * p.width + 16;  // + the zero-tap tail of a padded quad
+  const int64_t lo = T0 < 0 ? 0 : T0;
+  int64_t hi = T0 + span;
+  if (hi > p.length) hi = p.length;
+  if (hi < lo) hi = lo;
+  const int64_t lo_a = lo + ((4 - ((a0 + lo) & 3)) & 3);
+  const int64_t hi_a = hi - ((a0 + hi) & 3);
+  const int q_lo = (int)(lo - T0) + shift, q_hi = (int)(hi - T0) + shift;
+  if (q_lo > 0 && T0 < 0)
+    for (int q = tid; q < q_lo; q += nthreads) xs[q] = 0.f;
+  if (hi < T0 + span)
+    for (int q = q_hi + tid; q < p.slot_floats; q += nthreads) xs[q] = 0.f;
+  if (hi_a > lo_a) {
+    const int head = (int)(lo_a - lo), tail = (int)(hi - hi_a);
+    if (tid < head) xs[q_lo + tid] = x[lo + tid];
+    else if (tid >= 32 && tid < 32 + tail) xs[(int)(hi_a - T0) + shift + (tid - 32)] = x[hi_a + (tid - 32)];
+  } else {
+    for (int q = q_lo + tid; q < q_hi; q += nthreads) xs[q] = x[T0 + q - shift];
+  }
+  if (tid == 0) {
+    if (hi_a > lo_a) {
+      const int64_t n_al = hi_a - lo_a;                                   // multiple of 4 floats
+      const int64_t chunk = ((n_al / 4 + p.csize - 1) / p.csize) * 4;     // floats per CTA, multiple of 4
+      mbar_expect_tx(full, (uint32_t)n_al * 4u);                          // the whole body lands in every CTA
+      const int64_t c0 = lo_a + (int64_t)crank * chunk;
+      int64_t c1 = c0 + chunk;
+      if (c1 > hi_a) c1 = hi_a;
+      if (c1 > c0)
+        bulk_g2s_multicast(xs + (c0 - T0) + shift, x + c0, (uint32_t)(c1 - c0) * 4u, full, (uint16_t)((1u << p.csize) - 1u));
+    } else {
+      mbar_arrive(full);
+    }
+  }
+}
+__device__ __forceinline__ int r3_shift(const R3Params& p, int64_t row, int64_t f0) {
+  const int64_t T0 = f0 * p.orig_r - p.width;
+  const int a0 = (int)((reinterpret_cast<uintptr_t>(p.wave + row * p.row_stride) >> 2) & 3);
+  return (int)((((a0 + T0) % 4) + 4) % 4);
+}
+
+__global__ void __maxnreg__(200) resample_r3_kernel(const R3Params p, int require_flag) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_x = reinterpret_cast<float*>(smem_raw);                                   // [3][slot_floats]
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_x + 3 * (size_t)p.slot_floats);   // [3]
+  uint64_t* s_empty = s_full + 3;                                                    // [3]
+  if (require_flag && p.hdr->r3_ok == 0) return;  // (uniform over the grid) the mma kernel launched next does the work
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t crank = cluster_ctarank();
+  const int64_t cid = blockIdx.x / p.csize, n_clusters = gridDim.x / p.csize;
+  if (tid < 3) {
+    mbar_init(s_full + tid, 1);
+    mbar_init(s_empty + tid, p.csize);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  cluster_sync_all();  // every CTA's barriers exist before anyone multicasts into it or arrives on it
+
+  // this warp's quad of phases and its taps (registers for the rest of the kernel)
+  const int quad = (int)crank * kR3Warps + warp;
+  const bool active = quad < p.n_quads;
+  float4 tp[kR3Len];
+  int qb = 0;
+  if (active) {
+    qb = p.qbase[quad];
+#pragma unroll
+    for (int i = 0; i < kR3Len; ++i) tp[i] = __ldg(p.qtaps + (size_t)quad * kR3Len + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kR3Len; ++i) tp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int j0 = 4 * quad;
+
+  // tiles of this cluster: T(n) = cid + n * n_clusters
+  auto tile_of = [&](int64_t n, int64_t& row, int64_t& f0) {
+    const int64_t t = cid + n * n_clusters;
+    row = t / p.tiles_per_row;
+    f0 = (t - row * p.tiles_per_row) * 32;
+    return t < p.total_tiles;
+  };
+  int64_t row, f0;
+  for (int64_t n = 0; n < 2; ++n)  // prologue: two tiles in flight
+    if (tile_of(n, row, f0)) r3_fill(p, row, f0, s_x + (size_t)(n % 3) * p.slot_floats, s_full + (n % 3), crank, tid, blockDim.x);
+  __syncthreads();
+  for (int64_t n = 0; tile_of(n, row, f0); ++n) {
+    const int slot = (int)(n % 3);
+    {  // stage tile n + 2 into the slot tile n - 1 used: every CTA of the cluster must have released it
+      int64_t nrow, nf0;
+      if (tile_of(n + 2, nrow, nf0)) {
+        const int ns = (int)((n + 2) % 3);
+        if (n + 2 >= 3 && tid == 0) mbar_wait_cluster(s_empty + ns, (uint32_t)(((n + 2) / 3 - 1) & 1));
+        __syncthreads();  // (the local scalar part may be written now too)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        r3_fill(p, nrow, nf0, s_x + (size_t)ns * p.slot_floats, s_full + ns, crank, tid, blockDim.x);
+      }
+    }
+    mbar_wait_cluster(s_full + slot, (uint32_t)((n / 3) & 1));
+    if (active) {
+      const float* xs = s_x + (size_t)slot * p.slot_floats + r3_shift(p, row, f0) + lane * p.orig_r + qb;
+      uint64_t a01e = 0ull, a23e = 0ull, a01o = 0ull, a23o = 0ull;
+#pragma unroll
+      for (int i = 0; i < kR3Len; i += 2) {
+        const float x0 = xs[i], x1 = xs[i + 1];
+        a01e = fma2_raw(pk2(tp[i].x, tp[i].y), pk2(x0, x0), a01e);
+        a23e = fma2_raw(pk2(tp[i].z, tp[i].w), pk2(x0, x0), a23e);
+        a01o = fma2_raw(pk2(tp[i + 1].x, tp[i + 1].y), pk2(x1, x1), a01o);
+        a23o = fma2_raw(pk2(tp[i + 1].z, tp[i + 1].w), pk2(x1, x1), a23o);
+      }
+      const float2 y01 = upk2(add2_raw(a01e, a01o)), y23 = upk2(add2_raw(a23e, a23o));
+      const int64_t f = f0 + lane;
+      if (f < p.frames) {
+        const int64_t n0 = f * p.new_r + j0;
+        float* o = p.out + row * p.out_row_stride + n0;
+        if (p.out_vec && j0 + 4 <= p.new_r && n0 + 4 <= p.out_len) {
+          *reinterpret_cast<float4*>(o) = make_float4(y01.x, y01.y, y23.x, y23.y);
+        } else {
+          const float y[4] = {y01.x, y01.y, y23.x, y23.y};
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            if (j0 + r < p.new_r && n0 + r < p.out_len) o[r] = y[r];
+        }
+      }
+    }
+    __syncthreads();  // this CTA is done with the slot ...
+    if (tid == 0)     // ... tell every CTA of the cluster (they multicast into it)
+      for (uint32_t r = 0; r < (uint32_t)p.csize; ++r) mbar_arrive_remote(s_empty + slot, r);
+  }
+  cluster_sync_all();  // nobody leaves while a peer may still arrive on its barriers
+}
+
 // Straightforward one-output-per-thread kernel (any ratio).  Consecutive threads are consecutive
 // output samples, i.e. consecutive phases of the same input neighbourhood: input loads hit L1.
 __global__ void __launch_bounds__(256)
@@ -696,6 +942,9 @@ int resample_prepare_impl(const float* kernel, int orig_r, int new_r, int width,
                                                 reinterpret_cast<RsTile*>(base + l.tiles),
                                                 reinterpret_cast<float4*>(base + l.frags),
                                                 reinterpret_cast<uint4*>(base + l.frags16));
+  resample_r3_plan_kernel<<<1, 256, 0, stream>>>(kernel, support, new_r, taps, (new_r + 3) / 4, hdr,
+                                                 reinterpret_cast<int*>(base + l.r3base),
+                                                 reinterpret_cast<float4*>(base + l.r3taps));
   resample_simt_plan_kernel<<<1, 256, 0, stream>>>(kernel, support, new_r, taps, rs_tiles(new_r), hdr,
                                                    reinterpret_cast<RsSimtGroup*>(base + l.sgroups),
                                                    reinterpret_cast<float*>(base + l.staps));
@@ -712,15 +961,84 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
   const RsLayout l = rs_layout(new_r, taps);
   const unsigned char* base = static_cast<const unsigned char*>(ws);
 
-  // B200A_RS=simt|mma|direct forces one kernel family (A/B measurements, tests); default: the first that applies
+  // B200A_RS=simt|mma|bf16|direct forces one kernel family (A/B measurements, tests); default: the first that applies
   static const int forced = [] {
     const char* e = std::getenv("B200A_RS");
     if (e == nullptr) return 0;
-    return e[0] == 's' ? 1 : (e[0] == 'm' ? 2 : (e[0] == 'd' ? 3 : 0));
+    return e[0] == 's' ? 1 : (e[0] == 'm' ? 2 : (e[0] == 'd' ? 3 : (e[0] == 'b' ? 4 : (e[0] == 'r' ? 5 : 0))));
   }();
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     return B200A_ECUDA;
+
+  // ---- cluster path: taps in registers, tiles multicast to the CTAs that share the phases --------------------------
+  bool r3_launched = false;
+  {
+    const int n_quads = (new_r + 3) / 4;
+    int csize = 1;
+    while (csize * kR3Warps < n_quads) csize *= 2;
+    const int slot_floats = (32 * orig_r + 2 * width + 16 + 3 + 3 + kR3Len) & ~3;
+    const size_t smem = sizeof(float) * 3 * (size_t)slot_floats + 64;
+    const bool want = forced == 5 || (forced == 0 && (orig_r & 1) == 1 && n_quads >= 8);
+    if (want && csize <= kR3MaxCluster && smem <= (size_t)227 * 1024 && (reinterpret_cast<uintptr_t>(wave) & 3) == 0 &&
+        length + (int64_t)taps + 64 * (int64_t)orig_r < ((int64_t)1 << 31)) {
+      R3Params p{};
+      p.wave = wave;
+      p.rows = rows;
+      p.length = length;
+      p.row_stride = row_stride;
+      p.out = out;
+      p.out_row_stride = out_row_stride;
+      p.out_len = out_len;
+      p.hdr = reinterpret_cast<const RsHeader*>(base + l.header);
+      p.qbase = reinterpret_cast<const int*>(base + l.r3base);
+      p.qtaps = reinterpret_cast<const float4*>(base + l.r3taps);
+      p.orig_r = orig_r;
+      p.new_r = new_r;
+      p.width = width;
+      p.n_quads = n_quads;
+      p.csize = csize;
+      p.frames = (out_len + new_r - 1) / new_r;
+      p.tiles_per_row = (p.frames + 31) / 32;
+      p.total_tiles = rows * p.tiles_per_row;
+      p.slot_floats = slot_floats;
+      p.out_vec = (new_r % 4 == 0 && out_row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+      if (cudaFuncSetAttribute(resample_r3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        return B200A_ECUDA;
+      cudaLaunchConfig_t cfg{};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)csize;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.blockDim = dim3(kR3Warps * 32, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cfg.gridDim = dim3((unsigned)csize, 1, 1);
+      int max_clusters = 0;
+      const cudaError_t occ = cudaOccupancyMaxActiveClusters(&max_clusters, resample_r3_kernel, &cfg);
+      if (std::getenv("B200A_DEBUG") != nullptr)
+        std::fprintf(stderr, "[b200a] r3: csize=%d smem=%zu occupancy query: %s, max_clusters=%d\n", csize, smem,
+                     cudaGetErrorString(occ), max_clusters);
+      if (occ == cudaSuccess && max_clusters > 0) {
+        int64_t n_clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
+        if (n_clusters < 1) n_clusters = 1;
+        cfg.gridDim = dim3((unsigned)(n_clusters * csize), 1, 1);
+        const int require_flag = forced == 5 ? 0 : 1;
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, resample_r3_kernel, p, require_flag);
+        if (std::getenv("B200A_DEBUG") != nullptr)
+          std::fprintf(stderr, "[b200a] r3: launch %u CTAs: %s\n", cfg.gridDim.x, cudaGetErrorString(le));
+        if (le != cudaSuccess) return B200A_ECUDA;
+        if (forced == 5) return launch_status();
+        r3_launched = true;  // the tensor-pipe kernel below runs only if the plan says the quads did not fit
+      } else {
+        (void)cudaGetLastError();
+      }
+    }
+    if (forced == 5 && !r3_launched) return B200A_EUNSUPPORTED;
+  }
 
   // ---- packed-FP32 SIMT path: odd orig' (conflict-free frame-per-lane reads) and the 3-slot ring fits -------------
   {
@@ -801,8 +1119,9 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
     // device-side step count with the room granted here), otherwise they are read through L1
     p.frag_smem_bytes = (int)(((size_t)kRsSmemBudget - smem_fixed) & ~(size_t)511);  // everything that is left
     const size_t smem = smem_fixed + p.frag_smem_bytes;
-    // B200A_RS=mma keeps the TF32 x 3 arithmetic; the default is the bf16 x 3 variant (half the tensor-pipe time)
-    auto kern = forced == 2 ? resample_mma_kernel<false> : resample_mma_kernel<true>;
+    // default: TF32 x 3 (2^-21 relative).  B200A_RS=bf16 selects the bf16 x 3 variant: measured 5 % faster at config 3
+    // (0.371 vs 0.391 ms) for 30x the rounding error, so it stays opt-in
+    auto kern = forced == 4 ? resample_mma_kernel<true> : resample_mma_kernel<false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return B200A_ECUDA;
     int64_t grid = p.total_blocks < sms ? p.total_blocks : sms;
@@ -821,6 +1140,7 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
       if (worst < best_conf) { best_conf = worst; best_spread = spread; }
     }
     p.row_spread = best_spread;
+    p.skip_if_r3_ok = r3_launched ? 1 : 0;
     // warps: n_tiles items (phase groups) per tile; prefer the largest count that divides them evenly
     const int items = n_tiles;
     int warps = 8;

@@ -631,3 +631,52 @@ class PitchShift(torch.nn.Module):
         else:
             shifted = torch.nn.functional.pad(shifted, [0, ori_len - shift_len])
         return shifted.reshape(shape[:-1] + shifted.shape[-1:])
+
+
+# ---- B200A_REFERENCE=1: A/B switch to the reference implementation (debugging only, never silent) -----------------
+# "an explicit env override to run the reference for A/B".  With the variable set when this module is
+# imported, every transform above keeps its constructor, attributes and buffers but `forward` runs the importable
+# `torchaudio.transforms` class of the same name with the same constructor arguments and THIS module's buffers (on
+# whatever device the input lives, CPU included).  A warning is issued at import; nothing is switched implicitly.
+def _install_reference_switch() -> None:
+    import os
+
+    if os.environ.get("B200A_REFERENCE", "0") != "1":
+        return
+    try:
+        import torchaudio.transforms as ref_T
+    except Exception as exc:  # noqa: BLE001
+        raise ImportError("B200A_REFERENCE=1 needs an importable torchaudio to route the transforms to") from exc
+    warnings.warn(
+        "B200A_REFERENCE=1: audio_b200.transforms modules run torchaudio's reference implementation "
+        f"(torchaudio {getattr(__import__('torchaudio'), '__version__', '?')}); the B200 kernels are bypassed",
+        stacklevel=2,
+    )
+
+    def patch(cls, ref_cls):
+        orig_init = cls.__init__
+
+        def __init__(self, *args, **kwargs):
+            orig_init(self, *args, **kwargs)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                self.__dict__["_reference_module"] = ref_cls(*args, **kwargs)  # not a registered sub-module
+
+        def forward(self, *args, **kwargs):
+            ref = self.__dict__["_reference_module"]
+            dev = next((a.device for a in args if isinstance(a, Tensor)), None)
+            if dev is not None:
+                ref.to(dev)
+            own = {k: v.to(dev) if dev is not None else v for k, v in self.state_dict().items()}
+            ref.load_state_dict(own, strict=False)  # the buffers the user sees / edits are the ones used
+            return ref(*args, **kwargs)
+
+        cls.__init__ = __init__
+        cls.forward = forward
+
+    for name in __all__:
+        if hasattr(ref_T, name):
+            patch(globals()[name], getattr(ref_T, name))
+
+
+_install_reference_switch()

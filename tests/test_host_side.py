@@ -251,3 +251,32 @@ def test_bench_reference_arm_contract():
     assert rec["metric"] == "MelSpectrogram frames/sec" and rec["unit"] == "frames/s" and rec["value"] > 0
     assert rec["cpu_baseline"]["kind"] in ("reference", "port") and rec["cpu_baseline"]["cores"] >= 1
     assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_switch_routes_modules_to_torchaudio():
+    """B200A_REFERENCE=1 (read at import) runs the reference class behind the same surface, loudly (warning)."""
+    import subprocess
+    import sys
+
+    pytest.importorskip("torchaudio")
+    code = r"""
+import sys, warnings
+sys.path.insert(0, sys.argv[1])
+import torch
+with warnings.catch_warnings(record=True) as w:
+    warnings.simplefilter("always")
+    import audio_b200.transforms as T
+assert any("B200A_REFERENCE" in str(x.message) for x in w), "the switch must announce itself"
+import torchaudio.transforms as R
+x = torch.randn(2, 4000, generator=torch.Generator().manual_seed(0))
+m = T.MelSpectrogram(16000, n_fft=400, hop_length=160, n_mels=40)
+assert torch.equal(m(x), R.MelSpectrogram(16000, n_fft=400, hop_length=160, n_mels=40)(x))   # CPU input: reference path
+m.spectrogram.window.mul_(0.5)  # the module's own buffers are what the reference run uses
+assert torch.allclose(m(x), 0.25 * R.MelSpectrogram(16000, n_fft=400, hop_length=160, n_mels=40)(x), rtol=1e-5)
+r = T.Resample(44100, 16000)
+assert torch.equal(r(x), R.Resample(44100, 16000)(x))
+print("ok")
+"""
+    env = dict(os.environ, B200A_REFERENCE="1")
+    out = subprocess.run([sys.executable, "-c", code, ROOT], env=env, capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

@@ -1,4 +1,7 @@
-"""Sweep B200A_SKEW (start-up stagger of the transform warps) in sub-processes: C2 mel, Spectrogram, C5 512/256."""
+"""A/B timing of library builds / env switches in sub-processes: C2 mel, Spectrogram, C5 512/256, MFCC, resample.
+
+    python tools/ab_time.py NAME=VALUE[,NAME=VALUE] ...     e.g.  B200A_LIB=audio_b200/build/libb200audio_w0.so  B200A_TC=0
+Each argument is one run with those environment variables set ("-" = no change)."""
 import json
 import os
 import subprocess
@@ -29,6 +32,8 @@ with warnings.catch_warnings():
             "spec1024": T.Spectrogram(n_fft=1024, hop_length=256),
             "mel512": T.MelSpectrogram(16000, n_fft=512, hop_length=128, n_mels=80),
             "mel256": T.MelSpectrogram(16000, n_fft=256, hop_length=64, n_mels=80),
+            "spec256": T.Spectrogram(n_fft=256, hop_length=64),
+            "mel2048": T.MelSpectrogram(16000, n_fft=2048, hop_length=512, n_mels=80),
             "mfcc": T.MFCC(16000, n_mfcc=40, melkwargs=dict(n_fft=1024, hop_length=256, n_mels=80))}
 with torch.inference_mode():
     for k, m in mods.items():
@@ -37,7 +42,11 @@ with torch.inference_mode():
 print(json.dumps(out))
 """
 
-for skew in [int(a) for a in sys.argv[1:]] or [0, 1000, 2000, 3000, 4000, 6000]:
-    env = dict(os.environ, B200A_SKEW=str(skew))
+for spec in sys.argv[1:] or ["-"]:
+    env = dict(os.environ)
+    if spec != "-":
+        for kv in spec.split(","):
+            k, v = kv.split("=", 1)
+            env[k] = os.path.abspath(v) if k == "B200A_LIB" else v
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
-    print("skew", skew, r.stdout.strip() or r.stderr[-400:], flush=True)
+    print(spec, r.stdout.strip() or r.stderr[-400:], flush=True)
