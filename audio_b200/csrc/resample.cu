@@ -67,8 +67,8 @@ struct RsLayout {
 };
 
 constexpr int kR3Len = 44;      // taps per phase quad held in registers (34 live + 3 x 2.76 drift at 441:160, padded)
-constexpr int kR3Warps = 10;    // warps per CTA == phase quads per CTA
-constexpr int kR3MaxCluster = 4;
+constexpr int kR3Warps = 8;     // warps per CTA == phase quads per CTA (a multiple of 4: registers are granted per 4 warps)
+constexpr int kR3MaxCluster = 8;
 
 struct RsSimtGroup {  // one group of 8 phases for the SIMT kernel
   int base;  // first tap (xp-relative) any phase of the group uses
@@ -703,9 +703,10 @@ __global__ void resample_r3_plan_kernel(const float* __restrict__ kernel, const 
 //   registers (docs/KERNEL_NOTES.md).  Here a warp owns ONE quad of 4 output phases for the whole kernel and keeps
 //   its 4 x kR3Len taps in 176 registers; lanes are the 32 frames of a tile, so the only shared-memory traffic is one
 //   conflict-free 4-byte read per tap position, feeding two FFMA2 (4 phases) with the sample as the broadcast operand.
-//   160 phases = 40 quads need 40 such warps; 204 registers per thread allow 10 per SM, so a CLUSTER of 4 CTAs covers
-//   the phases and shares every staged tile: each CTA fetches a quarter of the tile's samples with ONE bulk copy that is
-//   MULTICAST into the same offset of all four CTAs' shared memory (every HBM byte is read once), through a 3-slot ring
+//   160 phases = 40 quads need 40 such warps; at ~200 registers per thread an SM holds 8 (registers are granted per 4
+//   warps: 10 x 200 does not fit), so a CLUSTER of 5 CTAs covers the phases and shares every staged tile: each CTA
+//   fetches a fifth of the tile's samples with ONE bulk copy that is MULTICAST into the same offset of all the CTAs'
+//   shared memory (every HBM byte is read once), through a 3-slot ring
 //   with cluster-scope full / empty mbarriers.
 // ================================================================================================
 struct R3Params {
@@ -808,7 +809,7 @@ __device__ __forceinline__ int r3_shift(const R3Params& p, int64_t row, int64_t 
   return (int)((((a0 + T0) % 4) + 4) % 4);
 }
 
-__global__ void __maxnreg__(200) resample_r3_kernel(const R3Params p, int require_flag) {
+__global__ void __maxnreg__(224) resample_r3_kernel(const R3Params p, int require_flag) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_x = reinterpret_cast<float*>(smem_raw);                                   // [3][slot_floats]
   uint64_t* s_full = reinterpret_cast<uint64_t*>(s_x + 3 * (size_t)p.slot_floats);   // [3]
@@ -975,11 +976,10 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
   bool r3_launched = false;
   {
     const int n_quads = (new_r + 3) / 4;
-    int csize = 1;
-    while (csize * kR3Warps < n_quads) csize *= 2;
+    const int csize = (n_quads + kR3Warps - 1) / kR3Warps;  // CTAs that share a tile: 5 at 441:160
     const int slot_floats = (32 * orig_r + 2 * width + 16 + 3 + 3 + kR3Len) & ~3;
     const size_t smem = sizeof(float) * 3 * (size_t)slot_floats + 64;
-    const bool want = forced == 5 || (forced == 0 && (orig_r & 1) == 1 && n_quads >= 8);
+    const bool want = forced == 5;  // measured 1.80 ms at config 3 (cluster-scope barrier latency per 32-frame tile): opt-in only
     if (want && csize <= kR3MaxCluster && smem <= (size_t)227 * 1024 && (reinterpret_cast<uintptr_t>(wave) & 3) == 0 &&
         length + (int64_t)taps + 64 * (int64_t)orig_r < ((int64_t)1 << 31)) {
       R3Params p{};
