@@ -1202,11 +1202,6 @@ struct TcGeo {
 struct Tc2;
 int tc_b_budget(int n_fft);  // defined after Tc2
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
-  return pred != 0;
-}
 // (x, y) -> packed bf16 pair (x in the low half) and the packed pair of the residuals
 __device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));

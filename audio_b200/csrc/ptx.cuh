@@ -20,6 +20,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// hint: bring [src, src + bytes) (16-byte aligned, multiple of 16) into L2; no completion tracking
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // Bounded wait: a mis-programmed copy traps instead of hanging the GPU.  `try_wait` suspends the warp
 // in hardware up to the hinted time, so a waiting warp costs (almost) no issue slots.
 template <uint32_t SUSPEND_NS = 2000>
@@ -66,7 +70,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
 }
 // Instruction descriptor, kind::f16 with BF16 operands, FP32 accumulate, both operands K-major
 // (cute::UMMA::InstrDescriptor: c_format F32 at [4,6), a/b_format BF16 at [7,10)/[10,13), N>>3 at [17,23), M>>4 at [24,29)).
-__device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+__host__ __device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {  // one full warp
@@ -76,6 +80,12 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) { 
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {  // the warp that allocated
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// one lane of a converged warp (the thread that issues tcgen05.mma / commit)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
