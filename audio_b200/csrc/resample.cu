@@ -1510,7 +1510,7 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
   const RsLayout l = rs_layout(new_r, taps);
   const unsigned char* base = static_cast<const unsigned char*>(ws);
 
-  // B200A_RS=simt|mma|bf16|direct forces one kernel family (A/B measurements, tests); default: the first that applies
+  // B200A_RS=tc|simt|mma|bf16|direct|r3 forces one kernel family (A/B measurements, tests); default: the first that applies
   static const int forced = [] {
     const char* e = std::getenv("B200A_RS");
     if (e == nullptr) return 0;
@@ -1592,7 +1592,10 @@ int resample_run_impl(const void* ws, const float* kernel, int orig_r, int new_r
   {
     const RsTcSmem tcm = rs_tc_smem(orig_r, taps);
     const size_t smem = (size_t)tcm.total;
-    const bool want = forced == 6;
+    // default for odd orig' (conflict-free frame-per-lane reads) whenever the plan fits: 0.283 vs 0.391 ms at config 3.
+    // Chosen by the RATIO alone, never by the batch, so that a row's result does not depend on what it is batched with.
+    // bf16 x 3 arithmetic: ~6e-6 of the output peak against ~1e-6 for the TF32 x 3 kernel below.
+    const bool want = forced == 6 || (forced == 0 && (orig_r & 1) != 0);
     const RsTcSteps steps = rs_tc_steps(orig_r, new_r, width);
     if (want && steps.ok &&
         (reinterpret_cast<uintptr_t>(wave) & 3) == 0 && length + (int64_t)taps + 64 * (int64_t)orig_r < ((int64_t)1 << 31)) {

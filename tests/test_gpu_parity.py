@@ -325,7 +325,8 @@ def test_config3_full_size_properties():
     assert torch.isfinite(y).all()
     # linearity, row independence
     a = r(x[:4] * 3.0 - x[4:8])
-    assert torch.allclose(a, 3.0 * y[:4] - y[4:8], atol=2e-5)
+    # (bf16 x 3 tensor-core kernel: ~6e-6 of the output peak per call; north-star tolerance 1e-4 relative)
+    assert torch.allclose(a, 3.0 * y[:4] - y[4:8], atol=1e-4)
     assert torch.equal(r(x[[5, 900]]), y[[5, 900]])
     # shifting the input by one polyphase period (441 samples) shifts the output by 160
     z = r(x[:2, 441:])
