@@ -44,8 +44,8 @@ WORKLOAD = "MelSpectrogram n_fft=1024 hop=256 n_mels=80, batch=256x16kHzx10s fp3
 ALGO_BYTES = 4 * (BATCH * LENGTH + BATCH * FRAMES * N_MELS) + 4 * (N_FFT + (N_FFT // 2 + 1) * N_MELS)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused kernel (ncu --set full capture):
 # the write-back of part of the 51 MB output is still in L2 at kernel end
-NCU_DRAM_BYTES = 199_229_440
-NCU_DRAM_SOURCE = "ncu --set full, profiles/r1_stft1024_v6.txt (dram read+write per launch)"
+NCU_DRAM_BYTES = 196_650_752
+NCU_DRAM_SOURCE = "ncu --set full, profiles/r2_mel_v3_tc2_prefetch.txt (dram read 163.99 MB + write 32.66 MB per launch)"
 
 
 def workload_config(world):
@@ -65,48 +65,111 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled while the GPU sections of the bench run."""
+    """SM clocks and throttle reasons (the fields of `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,
+    clocks_event_reasons.*`) sampled while the GPU sections of the bench run.
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Read through NVML inside this process (pynvml = nvidia_ml_py, the library nvidia-smi itself sits on); the nvidia-smi
+    BINARY (a driver attach per sample) is only the fallback when NVML cannot be imported.  ONE sampler per job
+    (rank 0) covers every GPU of the job, and it is PAUSED inside the launch-bound end-to-end section (sampled right
+    before and right after it): the e2e number of the same code moved between 3.04 ms (twice), 3.9, 12.4 and 32.8 ms
+    per step from box to box at N = 1 and was 6.75 ms at N = 8 with a sampler in every rank, against 4.35 ms in
+    tools/h2d_probe.py, which has no sampler.  The cause was not isolated inside the round's GPU budget; keeping
+    driver queries out of that 60 ms window removes the one suspect this file controls."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.rows, self._stop, self.index = [], threading.Event(), index
+    def __init__(self, indices, active=True, period=0.02):
+        self.rows, self._stop, self.indices, self.active = [], threading.Event(), list(indices), active
+        self.period, self.source, self._nvml, self._handles = period, None, None, []
+        self._paused, self._lock = threading.Event(), threading.Lock()
         self._t = threading.Thread(target=self._run, daemon=True)
+
+    def pause(self):
+        """No query is in flight or will start until resume(): the launch-bound end-to-end section is bracketed by
+        samples, not interleaved with them (a driver query next to 12 CUDA API calls per 3 ms step is measurable)."""
+        self._paused.set()
+        with self._lock:
+            pass
+
+    def resume(self):
+        self._paused.clear()
+
+    def _open_nvml(self):
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            for i in self.indices:
+                p = torch.cuda.get_device_properties(i)
+                bdf = f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+                try:
+                    self._handles.append(pynvml.nvmlDeviceGetHandleByPciBusId(bdf.encode()))
+                except Exception:
+                    self._handles.append(pynvml.nvmlDeviceGetHandleByIndex(i))
+            self._nvml, self.source = pynvml, "NVML (pynvml) in-process"
+        except Exception:
+            self._nvml, self._handles, self.source = None, [], "nvidia-smi subprocess"
+
+    def _sample_nvml(self):
+        n = self._nvml
+        masks = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                 n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+        for h in self._handles:
+            sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+            reasons = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.rows.append([str(sm), str(mx)] + ["Active" if reasons & m else "Not Active" for m in masks])
+
+    def _sample_smi(self):
+        out = subprocess.run(
+            ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i",
+             ",".join(str(i) for i in self.indices)], capture_output=True, text=True, timeout=5).stdout.strip()
+        for line in out.splitlines():
+            if line.strip():
+                self.rows.append([c.strip() for c in line.split(",")])
 
     def _run(self):
         while not self._stop.is_set():
-            try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                    capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.02)
+            if self._paused.is_set():
+                self._stop.wait(0.002)
+                continue
+            with self._lock:
+                try:
+                    if self._nvml is not None:
+                        self._sample_nvml()
+                    else:
+                        self._sample_smi()
+                except Exception:
+                    pass
+            self._stop.wait(self.period if self._nvml is not None else max(self.period, 0.5))
 
     def __enter__(self):
-        self._t.start()
+        if self.active:
+            self._open_nvml()
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self.active:
+            self._t.join(timeout=6)
 
     def summary(self):
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "source": self.source}
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
-            for n, v in zip(names, r[3:7]):
+            for n, v in zip(self.NAMES, r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "samples": len(sm),
-                "reasons": sorted(reasons), "window": "headline timed region + e2e + configs sections"}
+                "reasons": sorted(reasons), "gpus": len(self.indices), "source": self.source,
+                "window": "headline timed region and configs sections; the e2e section is bracketed (sampler paused inside)"}
 
 
 # ---- the reference on the host ---------------------------------------------------------------------------------
@@ -255,7 +318,8 @@ def run_b200(args):
     x = torch.randn(BATCH, LENGTH, device=dev, generator=g)  # this rank's shard, resident in HBM
     configs = []
 
-    with torch.inference_mode(), ClockSampler(local) as clocks:
+    # rank 0 samples the clocks of every GPU of the job (local ranks 0 .. world - 1 on this one node)
+    with torch.inference_mode(), ClockSampler([local] if world == 1 else range(world), active=(rank == 0)) as clocks:
         # ---- headline: config 2, inputs resident -------------------------------------------------------------
         ms_step = time_steps(lambda: mel(x))
         y = mel(x)
@@ -274,6 +338,7 @@ def run_b200(args):
         for _ in range(2):
             e2e_step()
         pipe.join()
+        clocks.pause()  # sampled right before and right after this 60 ms section, not during it
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -283,6 +348,7 @@ def run_b200(args):
         e1.record()
         barrier()
         ms_e2e = e0.elapsed_time(e1) / K
+        clocks.resume()
         # the pipelined result is the same tensor the resident path produces
         assert torch.equal(yh.to(dev).transpose(-1, -2), y), "host pipeline result differs from resident result"
         del xh, yh, pipe

@@ -4,10 +4,9 @@ mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_n8.txt 2>&1
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
 timeout 300 python -m pytest tests -m gpu -q -k "sharded_mfcc" 2>&1 | tail -4 > gpurun_out/pytest_n8.txt
-timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n8_single.json 2>> gpurun_out/bench_n8.err
 python - <<'PY'
 import json
-for f in ("gpurun_out/bench_n8.json", "gpurun_out/bench_n8_single.json"):
+for f in ("gpurun_out/bench_n8.json",):
     try:
         b = json.load(open(f))
         print(f, "value", b["value"], "ms", b["ms_per_step"], "e2e", b["e2e"]["value"], b["e2e"]["ms_per_step"], b["e2e"].get("numa"))
