@@ -35,7 +35,7 @@ def main():
         if pat and not pat.search(name):
             continue
         demangled = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
-        short = re.sub(r"\(.*", "", demangled).replace("b200a::(anonymous namespace)::", "")
+        short = re.sub(r"\(.*", "", demangled.replace("(anonymous namespace)::", "")).replace("b200a::", "")
         print(short + "," + ",".join(str(c.get(k, 0)) for k in KEYS))
 
 
