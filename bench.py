@@ -39,6 +39,7 @@ BATCH, LENGTH = 256, 160000
 FRAMES = 1 + LENGTH // HOP  # 626
 RS_ROWS, RS_LEN, RS_ORIG, RS_NEW = 1024, 220500, 44100, 16000
 RS_OUT = 80000
+E2E_WINDOWS = 5
 WORKLOAD = "MelSpectrogram n_fft=1024 hop=256 n_mels=80, batch=256x16kHzx10s fp32 per GPU (BASELINE configs[1])"
 # compulsory traffic of the fused op = waveform in + features out + constant tables
 ALGO_BYTES = 4 * (BATCH * LENGTH + BATCH * FRAMES * N_MELS) + 4 * (N_FFT + (N_FFT // 2 + 1) * N_MELS)
@@ -339,15 +340,22 @@ def run_b200(args):
             e2e_step()
         pipe.join()
         clocks.pause()  # sampled right before and right after this 60 ms section, not during it
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(K):
-            e2e_step()
-        pipe.join()  # the current stream waits for the last device -> host copy
-        e1.record()
-        barrier()
-        ms_e2e = e0.elapsed_time(e1) / K
+        # E2E_WINDOWS windows of exactly K steps each, every one bracketed like the headline (barrier + sync on both sides,
+        # CUDA events, max over ranks); the MEDIAN window is reported and all of them are listed: a K-step window is only
+        # ~60 ms of launch-bound host work, and one stall of the host (another tenant, a driver query) multiplies it
+        e2e_windows = []
+        for _ in range(E2E_WINDOWS):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                e2e_step()
+            pipe.join()  # the current stream waits for the last device -> host copy
+            e1.record()
+            barrier()
+            e2e_windows.append(e0.elapsed_time(e1) / K)
+        e2e_windows = max_over_ranks(e2e_windows)
+        ms_e2e = sorted(e2e_windows)[len(e2e_windows) // 2]
         clocks.resume()
         # the pipelined result is the same tensor the resident path produces
         assert torch.equal(yh.to(dev).transpose(-1, -2), y), "host pipeline result differs from resident result"
@@ -419,7 +427,9 @@ def run_b200(args):
                              peak_source=peak_src, kernel="fused STFT+mel kernel (one launch per step)"),
             "e2e": {"value": frames_job / (ms_e2e * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": BATCH * LENGTH * 4, "d2h_bytes_per_step": BATCH * FRAMES * N_MELS * 4,
-                    "ms_per_step": ms_e2e, "api": "audio_b200.pipeline.HostPipeline(chunk_rows=64)",
+                    "ms_per_step": ms_e2e, "windows_ms_per_step": [round(w, 4) for w in e2e_windows],
+                    "estimator": f"median of {E2E_WINDOWS} windows of {K} steps",
+                    "api": "audio_b200.pipeline.HostPipeline(chunk_rows=64)",
                     "numa": numa},
             "gpu_launches": K,
             "clocks": clock_summary,
