@@ -280,3 +280,32 @@ print("ok")
     env = dict(os.environ, B200A_REFERENCE="1")
     out = subprocess.run([sys.executable, "-c", code, ROOT], env=env, capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_bench_clock_sampler_pause_and_fallback():
+    """bench.py's clock sampler: one per job, pausable (no query in flight inside the launch-bound e2e section), and a
+    summary that says where the numbers came from.  Without a GPU both NVML and nvidia-smi are absent: the sampler must
+    still start, pause, resume and stop cleanly."""
+    import importlib.util
+    import time
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.E2E_WINDOWS >= 3 and bench.E2E_WINDOWS % 2 == 1  # a median needs an odd count
+    with bench.ClockSampler([0], active=True, period=0.005) as c:
+        time.sleep(0.03)
+        c.pause()
+        n = len(c.rows)
+        time.sleep(0.03)
+        assert len(c.rows) == n  # nothing is sampled while paused
+        c.resume()
+    s = c.summary()
+    assert set(s) >= {"sm_mhz", "sm_max_mhz", "reasons", "source"}
+    with bench.ClockSampler(range(8), active=False) as idle:  # ranks other than 0
+        idle.pause()
+        idle.resume()
+    assert idle.rows == [] and not idle._t.is_alive()
+    # both arms describe the workload with the same words (the driver pairs their lines)
+    assert bench.workload_config(8)["global_batch"] == 8 * bench.BATCH
