@@ -74,6 +74,8 @@ _SIGNATURES = {
     "b200a_resample_width": (c_int32, [c_int32, c_int32, c_int32, c_double]),
     "b200a_resample_len": (c_int64, [c_int64, c_int32, c_int32]),
     "b200a_resample_support": (ctypes.c_int, [c_int32, c_int32, c_int32, c_double, c_int32, POINTER(c_int32), POINTER(c_int32)]),
+    "b200a_resample_plan_info": (ctypes.c_int, [c_int32, c_int32, c_int32, POINTER(c_int32)]),
+    "b200a_resample_tc_band": (ctypes.c_int, [c_int32, c_int32, c_int32, c_int32, POINTER(c_int32), POINTER(c_int32)]),
     "b200a_frontend_workspace_bytes": (c_size_t, [POINTER(FrontendDesc)]),
     "b200a_frontend_prepare": (
         ctypes.c_int,

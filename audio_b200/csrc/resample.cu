@@ -1473,6 +1473,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) resample_tc_kernel(const RsTcPa
 
 size_t resample_workspace_bytes_impl(int new_r, int taps) { return rs_layout(new_r, taps).total; }
 
+// Host-only: what resample_run_impl will launch for this ratio (nothing touches the device).
+//   info[0] kernel family: 1 tcgen05 (resample_tc_kernel), 2 mma.sync TF32 x 3, 3 direct
+//   info[1] bytes of the banded bf16 tap blocks of the tcgen05 plan (0 if it does not apply)
+//   info[2] dynamic shared memory of the tcgen05 kernel, info[3] its MMAs per 32-frame tile
+int resample_plan_info_impl(int orig_r, int new_r, int width, int32_t* info) {
+  if (orig_r < 1 || new_r < 1 || width < 0 || info == nullptr) return B200A_EINVAL;
+  const int taps = 2 * width + orig_r;
+  const RsTcSteps steps = rs_tc_steps(orig_r, new_r, width);
+  const RsTcSmem tcm = rs_tc_smem(orig_r, taps);
+  const bool tc = (orig_r & 1) != 0 && steps.ok != 0;
+  const int n_tiles = rs_tiles(new_r);
+  const int xs_floats = (kRsFrames * orig_r + taps + 16 + 4 + 3) & ~3;
+  const size_t smem_fixed = sizeof(float) * 2 * (size_t)xs_floats + 16 + sizeof(RsTile) * ((n_tiles + 3) & ~3);
+  const bool mma = n_tiles <= kRsMaxTiles && smem_fixed + 1024 <= (size_t)kRsSmemBudget;
+  info[0] = tc ? 1 : (mma ? 2 : 3);
+  info[1] = steps.ok ? steps.b_bytes : 0;
+  info[2] = steps.ok ? tcm.total : 0;
+  info[3] = steps.ok ? 2 * steps.steps + 1 : 0;
+  return B200A_OK;
+}
+
+// Host-only: the live-tap band [first, last] the tcgen05 plan assumes for output phase `phase` (see rs_tc_band).
+int resample_tc_band_impl(int orig_r, int new_r, int width, int phase, int32_t* first, int32_t* last) {
+  if (orig_r < 1 || new_r < 1 || width < 0 || phase < 0 || phase >= new_r || first == nullptr || last == nullptr)
+    return B200A_EINVAL;
+  int f, l;
+  rs_tc_band(phase, orig_r, new_r, width, f, l);
+  const int taps = 2 * width + orig_r;
+  *first = f;
+  *last = l < taps - 1 ? l : taps - 1;
+  return B200A_OK;
+}
+
 int resample_prepare_impl(const float* kernel, int orig_r, int new_r, int width, void* ws, size_t ws_bytes,
                           cudaStream_t stream) {
   if (kernel == nullptr || ws == nullptr || orig_r < 1 || new_r < 1 || width < 0) return B200A_EINVAL;

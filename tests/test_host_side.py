@@ -309,3 +309,38 @@ def test_bench_clock_sampler_pause_and_fallback():
     assert idle.rows == [] and not idle._t.is_alive()
     # both arms describe the workload with the same words (the driver pairs their lines)
     assert bench.workload_config(8)["global_batch"] == 8 * bench.BATCH
+
+
+@pytest.mark.parametrize("method", ["sinc_interp_hann", "sinc_interp_kaiser"])
+def test_resample_tc_band_covers_the_reference_kernels_support(method):
+    """The tcgen05 resampler's banded plan is computed on the host from (orig', new', width) alone and assumes that
+    phase j has live taps only inside (j orig'/new', j orig'/new' + 2 width).  Check that against the taps the
+    reference's own construction (functional.py:1359-1400, rebuilt bit-identically in _constants) really produces, with
+    the device's liveness rule (|k| > 1e-12 max|k| of the row) -- if the band were too narrow the device-side check would
+    silently send every call to the slower kernel."""
+    import ctypes
+
+    from audio_b200 import _constants as C
+    from audio_b200 import _lib
+
+    L = _lib.lib()
+    first, last = ctypes.c_int32(), ctypes.c_int32()
+    info = (ctypes.c_int32 * 4)()
+    for orig, new in [(44100, 16000), (48000, 16000), (16000, 8000), (22050, 16000), (44100, 48000), (8000, 16000),
+                      (16000, 44100), (11025, 8000), (32000, 44100), (10, 11), (11, 10)]:
+        g = math.gcd(orig, new)
+        k, width = C.sinc_resample_kernel(orig, new, g, resampling_method=method)
+        k = k[:, 0, :].double().numpy()
+        o, n = orig // g, new // g
+        assert k.shape == (n, 2 * width + o)
+        assert L.b200a_resample_plan_info(o, n, width, info) == 0 and info[0] in (1, 2, 3)
+        if info[0] == 1:
+            assert o % 2 == 1 and 0 < info[1] <= 64 * 1024 and info[2] <= 227 * 1024
+        for j in range(n):
+            assert L.b200a_resample_tc_band(o, n, width, j, ctypes.byref(first), ctypes.byref(last)) == 0
+            live = np.nonzero(np.abs(k[j]) > 1e-12 * np.abs(k[j]).max())[0]
+            assert first.value <= live.min() and live.max() <= last.value, (orig, new, j, first.value, last.value)
+            assert last.value - first.value <= 2 * width + 2  # and it is tight: at most two taps wider than 2 width
+    assert L.b200a_resample_plan_info(441, 160, 17, info) == 0 and info[0] == 1 and info[3] == 61  # config 3
+    assert L.b200a_resample_plan_info(2, 1, 13, info) == 0 and info[0] == 2  # even orig': the mma.sync kernel
+    assert L.b200a_resample_plan_info(0, 1, 13, info) != 0
